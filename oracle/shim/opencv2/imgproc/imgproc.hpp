@@ -1,0 +1,2 @@
+// oracle shim: intentionally empty (see ../core/core.hpp)
+#pragma once
