@@ -1,0 +1,37 @@
+# Top-level build: libsrcnn_b200.so (the product: CUDA kernels + C ABI), bin/srcnn (the drop-in CLI),
+# and the oracle checkers (test infrastructure).  sm_100a only; no other arch, no fallback.
+NVCC ?= /usr/local/cuda/bin/nvcc
+HOSTCXX := /usr/bin/g++
+HOSTCC := /usr/bin/gcc
+ARCH := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -ccbin $(HOSTCXX) -Xcompiler -fPIC,-fvisibility=hidden,-ffp-contract=off,-fno-fast-math \
+           --fmad=true -Xptxas -v -Wno-deprecated-gpu-targets
+CSRC := srcnn_cpp_b200/csrc
+OBJ := build/obj
+LIB := srcnn_cpp_b200/libsrcnn_b200.so
+WEIGHTS := $(abspath srcnn_cpp_b200/data/srcnn_weights.bin)
+CU := api color_bicubic srcnn_fp32 srcnn_tc
+OBJS := $(addprefix $(OBJ)/,$(addsuffix .o,$(CU))) $(OBJ)/weights_blob.o
+
+all: $(LIB) oracle
+
+$(OBJ)/%.o: $(CSRC)/%.cu $(CSRC)/common.h $(CSRC)/weights.h include/srcnn_b200.h
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(OBJ)/$*.ptxas.log || (cat $(OBJ)/$*.ptxas.log; false)
+	@grep -E "error|warning|spill|registers" $(OBJ)/$*.ptxas.log | grep -v "0 bytes spill" | head -40 || true
+
+$(OBJ)/weights_blob.o: $(CSRC)/weights_blob.c $(WEIGHTS)
+	@mkdir -p $(OBJ)
+	$(HOSTCC) -c -fPIC -DSRCNN_WEIGHTS_BIN='"$(WEIGHTS)"' $< -o $@
+
+$(LIB): $(OBJS)
+	$(NVCC) $(ARCH) -shared -ccbin $(HOSTCXX) -Xcompiler -fPIC -o $@ $(OBJS) -lcuda
+
+oracle:
+	$(MAKE) -C oracle
+
+clean:
+	rm -rf build $(LIB) bin
+	$(MAKE) -C oracle clean
+
+.PHONY: all oracle clean

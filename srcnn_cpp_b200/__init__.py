@@ -1,0 +1,274 @@
+"""srcnn_cpp_b200 -- Python front-end of libsrcnn_b200.so (the B200-native SRCNN_Cpp hot path).
+
+The product is the CUDA library behind the C ABI in include/srcnn_b200.h; this module is only the
+ctypes binding the tests and bench.py use (PyTorch supplies device buffers, streams and
+torch.distributed -- plumbing, not the product).  The reference's own host side is C++ and so is
+ours: cli/srcnn_main.cpp (bin/srcnn) and include/libsrcnn.h (ProcessSRCNN).
+
+There is NO CPU fallback and no import of oracle/: if the shared library is missing, or no sm_100
+device is present, construction fails loudly.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsrcnn_b200.so")
+
+VARIANT_TC = 0
+VARIANT_FP32 = 1
+ORDER_BGR = 0
+ORDER_RGB = 1
+
+OK = 0
+E_RATIO = -1
+E_ARG = -20
+E_NODEVICE = -30
+E_CUDA = -31
+E_NOMEM = -32
+E_KERNEL = -33
+
+# every symbol include/srcnn_b200.h declares (tests/test_abi.py checks the library exports them all)
+ABI_SYMBOLS = [
+    "srcnn_abi_version", "srcnn_strerror", "srcnn_create", "srcnn_destroy", "srcnn_last_error",
+    "srcnn_set_variant", "srcnn_get_variant", "srcnn_set_stream", "srcnn_get_stream", "srcnn_sync",
+    "srcnn_launch_count", "srcnn_device_sm_count", "srcnn_profile_enable", "srcnn_profile_read", "srcnn_out_dims", "srcnn_host_alloc", "srcnn_host_free",
+    "srcnn_process_host", "srcnn_process_device", "srcnn_process_batch_device", "srcnn_process_batch_host",
+    "srcnn_band_src_rows", "srcnn_process_band_device", "srcnn_stage_color_bicubic_device",
+    "srcnn_stage_cnn_device", "srcnn_stage_conv99x11_fp32_device", "srcnn_stage_merge_device",
+]
+
+
+class SrcnnError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__("srcnn status %d: %s" % (status, msg))
+        self.status = status
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen libsrcnn_b200.so and declare the C ABI.  Raises if the library has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FileNotFoundError(
+            LIB_PATH + " is missing: run `make` (or __graft_entry__.build()). There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, u8p, i32p, sz = C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.c_size_t
+    L.srcnn_abi_version.restype = C.c_int
+    L.srcnn_strerror.restype = C.c_char_p
+    L.srcnn_strerror.argtypes = [C.c_int]
+    L.srcnn_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int]
+    L.srcnn_destroy.argtypes = [vp]
+    L.srcnn_last_error.restype = C.c_char_p
+    L.srcnn_last_error.argtypes = [vp]
+    L.srcnn_set_variant.argtypes = [vp, C.c_int]
+    L.srcnn_get_variant.argtypes = [vp]
+    L.srcnn_set_stream.argtypes = [vp, vp]
+    L.srcnn_get_stream.restype = vp
+    L.srcnn_get_stream.argtypes = [vp]
+    L.srcnn_sync.argtypes = [vp]
+    L.srcnn_launch_count.restype = C.c_longlong
+    L.srcnn_launch_count.argtypes = [vp]
+    L.srcnn_device_sm_count.argtypes = [vp]
+    L.srcnn_profile_enable.argtypes = [vp, C.c_int]
+    L.srcnn_profile_read.argtypes = [vp, C.POINTER(C.c_double), i32p]
+    L.srcnn_out_dims.argtypes = [C.c_int, C.c_int, C.c_float, i32p, i32p]
+    L.srcnn_host_alloc.argtypes = [C.POINTER(vp), sz]
+    L.srcnn_host_free.argtypes = [vp]
+    L.srcnn_process_host.argtypes = [vp, u8p, C.c_int, C.c_int, sz, C.c_int, C.c_float, u8p, sz]
+    L.srcnn_process_device.argtypes = [vp, u8p, C.c_int, C.c_int, sz, C.c_int, C.c_float, u8p, sz]
+    L.srcnn_process_batch_device.argtypes = [vp, u8p, C.c_int, C.c_int, C.c_int, sz, sz, C.c_int, C.c_float, u8p, sz, sz]
+    L.srcnn_process_batch_host.argtypes = [vp, u8p, C.c_int, C.c_int, C.c_int, sz, sz, C.c_int, C.c_float, u8p, sz, sz]
+    L.srcnn_band_src_rows.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, i32p, i32p]
+    L.srcnn_process_band_device.argtypes = [vp, u8p, C.c_int, C.c_int, sz, C.c_int, C.c_int, C.c_int, C.c_float,
+                                            C.c_int, C.c_int, u8p, sz]
+    L.srcnn_stage_color_bicubic_device.argtypes = [vp, u8p, C.c_int, C.c_int, sz, C.c_int, C.c_float, u8p, u8p, u8p, sz]
+    L.srcnn_stage_cnn_device.argtypes = [vp, C.c_int, u8p, C.c_int, C.c_int, sz, u8p, sz]
+    L.srcnn_stage_conv99x11_fp32_device.argtypes = [vp, u8p, C.c_int, C.c_int, sz, vp]
+    L.srcnn_stage_merge_device.argtypes = [vp, u8p, u8p, u8p, C.c_int, C.c_int, sz, C.c_int, u8p, sz]
+    _lib = L
+    return L
+
+
+def out_dims(w, h, scale):
+    """(ow, oh) = ((int)((float)w*scale), (int)((float)h*scale)) -- src/srcnn.cpp:573-575."""
+    L = load_library()
+    ow, oh = C.c_int(), C.c_int()
+    rc = L.srcnn_out_dims(w, h, C.c_float(scale), C.byref(ow), C.byref(oh))
+    if rc != OK:
+        raise SrcnnError(rc, L.srcnn_strerror(rc).decode())
+    return ow.value, oh.value
+
+
+def band_src_rows(h, scale, r0, r1):
+    L = load_library()
+    s0, s1 = C.c_int(), C.c_int()
+    rc = L.srcnn_band_src_rows(h, C.c_float(scale), r0, r1, C.byref(s0), C.byref(s1))
+    if rc != OK:
+        raise SrcnnError(rc, L.srcnn_strerror(rc).decode())
+    return s0.value, s1.value
+
+
+class PinnedBuffer:
+    """Page-locked host memory from srcnn_host_alloc, viewed as a numpy uint8 array."""
+
+    def __init__(self, nbytes):
+        L = load_library()
+        p = C.c_void_p()
+        rc = L.srcnn_host_alloc(C.byref(p), nbytes)
+        if rc != OK:
+            raise SrcnnError(rc, "srcnn_host_alloc(%d)" % nbytes)
+        self.ptr = p.value
+        self.nbytes = nbytes
+        self.array = np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(p.value))
+
+    def free(self):
+        if self.ptr:
+            load_library().srcnn_host_free(self.ptr)
+            self.ptr = None
+            self.array = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def _dptr(t):
+    """device pointer of a torch CUDA uint8/float tensor (must be contiguous in its last dim)"""
+    return C.c_void_p(t.data_ptr())
+
+
+class Engine:
+    """One srcnn_ctx: a device, a stream, workspace and packed weights (include/srcnn_b200.h)."""
+
+    def __init__(self, device=0, variant=VARIANT_TC, stream=None):
+        self.L = load_library()
+        self.ctx = C.c_void_p()
+        rc = self.L.srcnn_create(C.byref(self.ctx), int(device), int(variant))
+        if rc != OK:
+            self.ctx = None
+            raise SrcnnError(rc, self.L.srcnn_strerror(rc).decode())
+        self.device = int(device)
+        if stream is not None:
+            self.set_stream(stream)
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.L.srcnn_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != OK:
+            raise SrcnnError(rc, (self.L.srcnn_last_error(self.ctx) or b"").decode() or self.L.srcnn_strerror(rc).decode())
+
+    # -- context knobs ---------------------------------------------------------------------------
+    def set_variant(self, variant):
+        self._check(self.L.srcnn_set_variant(self.ctx, int(variant)))
+
+    def set_stream(self, cuda_stream_ptr):
+        """cuda_stream_ptr: int (cudaStream_t), e.g. torch.cuda.current_stream().cuda_stream; 0/None = own stream"""
+        self._check(self.L.srcnn_set_stream(self.ctx, C.c_void_p(cuda_stream_ptr or None)))
+
+    def sync(self):
+        self._check(self.L.srcnn_sync(self.ctx))
+
+    def profile_enable(self, on=True):
+        self._check(self.L.srcnn_profile_enable(self.ctx, 1 if on else 0))
+
+    def profile_read(self):
+        """-> ([ms colour+bicubic, ms fused SRCNN, ms merge], number of whole-path calls)"""
+        ms = (C.c_double * 3)()
+        n = C.c_int()
+        self._check(self.L.srcnn_profile_read(self.ctx, ms, C.byref(n)))
+        return [ms[0], ms[1], ms[2]], n.value
+
+    @property
+    def launches(self):
+        return int(self.L.srcnn_launch_count(self.ctx))
+
+    @property
+    def sm_count(self):
+        return int(self.L.srcnn_device_sm_count(self.ctx))
+
+    # -- whole path, host buffers (numpy) ----------------------------------------------------------
+    def process(self, img, scale, order=ORDER_BGR, out=None):
+        """img: HxWx3 uint8 numpy array (BGR by default, like cv::imread).  Returns OHxOWx3 uint8."""
+        img = np.asarray(img)
+        if img.ndim != 3 or img.shape[2] != 3 or img.dtype != np.uint8:
+            raise SrcnnError(E_ARG, "expected an HxWx3 uint8 image")
+        if not img.flags.c_contiguous:
+            img = np.ascontiguousarray(img)
+        h, w, _ = img.shape
+        ow, oh = out_dims(w, h, scale)
+        if out is None:
+            out = np.empty((oh, ow, 3), np.uint8)
+        self._check(self.L.srcnn_process_host(self.ctx, img.ctypes.data, w, h, img.strides[0], order, C.c_float(scale),
+                                              out.ctypes.data, out.strides[0]))
+        return out
+
+    def process_batch(self, frames, scale, order=ORDER_BGR, out=None):
+        """frames: NxHxWx3 uint8 numpy array -> NxOHxOWx3."""
+        frames = np.ascontiguousarray(frames)
+        n, h, w, _ = frames.shape
+        ow, oh = out_dims(w, h, scale)
+        if out is None:
+            out = np.empty((n, oh, ow, 3), np.uint8)
+        self._check(self.L.srcnn_process_batch_host(self.ctx, frames.ctypes.data, n, w, h, frames.strides[1],
+                                                    frames.strides[0], order, C.c_float(scale), out.ctypes.data,
+                                                    out.strides[1], out.strides[0]))
+        return out
+
+    # -- whole path, device buffers (torch CUDA tensors) -------------------------------------------
+    def process_device(self, src, scale, dst, order=ORDER_BGR):
+        h, w, _ = src.shape
+        self._check(self.L.srcnn_process_device(self.ctx, _dptr(src), w, h, src.stride(0), order, C.c_float(scale),
+                                                _dptr(dst), dst.stride(0)))
+        return dst
+
+    def process_batch_device(self, src, scale, dst, order=ORDER_BGR):
+        n, h, w, _ = src.shape
+        self._check(self.L.srcnn_process_batch_device(self.ctx, _dptr(src), n, w, h, src.stride(1), src.stride(0), order,
+                                                      C.c_float(scale), _dptr(dst), dst.stride(1), dst.stride(0)))
+        return dst
+
+    def process_band_device(self, src_rows, w, h, s0, s1, scale, r0, r1, dst_rows, order=ORDER_BGR):
+        """src_rows: (s1-s0)xWx3 device tensor holding source rows [s0,s1); dst_rows: (r1-r0)xOWx3."""
+        self._check(self.L.srcnn_process_band_device(self.ctx, _dptr(src_rows), w, h, src_rows.stride(0), s0, s1, order,
+                                                     C.c_float(scale), r0, r1, _dptr(dst_rows), dst_rows.stride(0)))
+        return dst_rows
+
+    # -- stages (torch CUDA tensors) ---------------------------------------------------------------
+    def stage_color_bicubic(self, src, scale, y, cr, cb, order=ORDER_BGR):
+        h, w, _ = src.shape
+        self._check(self.L.srcnn_stage_color_bicubic_device(self.ctx, _dptr(src), w, h, src.stride(0), order,
+                                                            C.c_float(scale), _dptr(y), _dptr(cr), _dptr(cb), y.stride(0)))
+
+    def stage_cnn(self, y, out, variant=None):
+        h, w = y.shape
+        v = self.L.srcnn_get_variant(self.ctx) if variant is None else variant
+        self._check(self.L.srcnn_stage_cnn_device(self.ctx, int(v), _dptr(y), w, h, y.stride(0), _dptr(out), out.stride(0)))
+        return out
+
+    def stage_conv99x11_fp32(self, y, act2):
+        h, w = y.shape
+        self._check(self.L.srcnn_stage_conv99x11_fp32_device(self.ctx, _dptr(y), w, h, y.stride(0), _dptr(act2)))
+        return act2
+
+    def stage_merge(self, y, cr, cb, dst, order=ORDER_BGR):
+        h, w = y.shape
+        self._check(self.L.srcnn_stage_merge_device(self.ctx, _dptr(y), _dptr(cr), _dptr(cb), w, h, y.stride(0), order,
+                                                    _dptr(dst), dst.stride(0)))
+        return dst

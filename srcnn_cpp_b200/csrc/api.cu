@@ -1,0 +1,471 @@
+// api.cu -- the C ABI of libsrcnn_b200.so (include/srcnn_b200.h): context, workspace, and the
+// host-side orchestration that replaces the timed body of the reference's pthreadcall()
+// (src/srcnn.cpp:505-659) with three kernel stages on one CUDA stream:
+//   K-A colour+bicubic  ->  K-B fused SRCNN (tcgen05 or strict FP32)  ->  K-C merge+colour back.
+// No CPU fallback exists anywhere in this file: every path ends in a kernel launch or an error.
+#include <cstdarg>
+#include <cstdlib>
+#include <new>
+
+#include "common.h"
+
+namespace srcnn {
+
+int fail(Ctx* c, int status, const char* fmt, ...) {
+    if (c) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(c->err, sizeof(c->err), fmt, ap);
+        va_end(ap);
+    }
+    return status;
+}
+
+int ensure(Ctx* c, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return SRCNN_OK;
+    if (b.p) {
+        SRCNN_CUDA(c, cudaStreamSynchronize(c->stream));
+        SRCNN_CUDA(c, cudaFree(b.p));
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    const size_t want = align_up(bytes + bytes / 8, 1 << 20);  // slack so slightly larger frames do not realloc
+    SRCNN_CUDA(c, cudaMalloc(&b.p, want));
+    b.cap = want;
+    return SRCNN_OK;
+}
+
+int prof_mark(Ctx* c) {
+    if (!c->profiling) return SRCNN_OK;
+    if (c->ev_used == c->ev_pool.size()) {
+        cudaEvent_t e;
+        SRCNN_CUDA(c, cudaEventCreate(&e));
+        c->ev_pool.push_back(e);
+    }
+    SRCNN_CUDA(c, cudaEventRecord(c->ev_pool[c->ev_used++], c->stream));
+    return SRCNN_OK;
+}
+
+static int scaled_dim(int n, float scale) {
+    // `newsz.width *= image_multiply` (src/srcnn.cpp:574-575): int -> float multiply -> truncation
+    return (int)((float)n * scale);
+}
+
+static int check_image(Ctx* c, const void* src, int w, int h, size_t stride, int order, float scale, const void* dst,
+                       size_t dst_stride, int* ow, int* oh) {
+    if (!c) return SRCNN_E_ARG;
+    if (!src || !dst) return fail(c, SRCNN_E_ARG, "null image pointer");
+    if (w <= 0 || h <= 0) return fail(c, SRCNN_E_ARG, "non-positive image size %dx%d", w, h);
+    if (stride < (size_t)w * 3) return fail(c, SRCNN_E_ARG, "source stride %zu < 3*w", stride);
+    if (order != SRCNN_ORDER_BGR && order != SRCNN_ORDER_RGB) return fail(c, SRCNN_E_ARG, "unknown channel order %d", order);
+    // src/srcnn.cpp:485-495 "ratio too small"
+    if (!(((float)w * scale) > 0.f) || !(((float)h * scale) > 0.f)) return fail(c, SRCNN_E_RATIO, "scale %g gives an empty image", scale);
+    *ow = scaled_dim(w, scale);
+    *oh = scaled_dim(h, scale);
+    if (*ow <= 0 || *oh <= 0) return fail(c, SRCNN_E_RATIO, "scale %g gives an empty image", scale);
+    if (dst_stride < (size_t)*ow * 3) return fail(c, SRCNN_E_ARG, "destination stride %zu < 3*ow", dst_stride);
+    return SRCNN_OK;
+}
+
+static int carve_planes(Ctx* c, int ow, int rows, int row0, Planes* pl) {
+    const size_t pitch = align_up((size_t)ow, 128);
+    const size_t plane = pitch * (size_t)rows;
+    int rc = ensure(c, c->plane_buf, plane * 4);
+    if (rc) return rc;
+    uint8_t* base = (uint8_t*)c->plane_buf.p;
+    pl->y = base;
+    pl->cr = base + plane;
+    pl->cb = base + 2 * plane;
+    pl->yout = base + 3 * plane;
+    pl->pitch = pitch;
+    pl->row0 = row0;
+    pl->rows = rows;
+    return SRCNN_OK;
+}
+
+static int run_cnn(Ctx* c, int variant, const CnnArgs& a) {
+    if (variant == SRCNN_VARIANT_FP32) return launch_cnn_fp32(c, a, nullptr);
+    if (variant == SRCNN_VARIANT_TC) return launch_cnn_tc(c, a);
+    return fail(c, SRCNN_E_ARG, "unknown variant %d", variant);
+}
+
+// rows [r0,r1) of the full output; d_src holds source rows [s0,s1); d_dst points at output row r0
+static int process_rows(Ctx* c, const uint8_t* d_src, int w, int h, size_t src_stride, int s0, int s1, int order,
+                        float scale, int ow, int oh, int r0, int r1, uint8_t* d_dst, size_t dst_stride) {
+    TapTable *tx, *ty;
+    int rc = get_taps(c, w, ow, &tx);
+    if (rc) return rc;
+    rc = get_taps(c, h, oh, &ty);
+    if (rc) return rc;
+    const int p0 = std::max(r0 - 6, 0), p1 = std::min(r1 + 6, oh);  // 6-px halo: 4 (conv1) + 2 (conv3)
+    Planes pl;
+    rc = carve_planes(c, ow, p1 - p0, p0, &pl);
+    if (rc) return rc;
+    // the band must bring every source row its taps touch
+    const int need0 = std::min(std::max(ty->h_ofs[p0] - 1, 0), h - 1);
+    const int need1 = std::min(std::max(ty->h_ofs[p1 - 1] + 2, 0), h - 1) + 1;
+    if (s0 > need0 || s1 < need1)
+        return fail(c, SRCNN_E_ARG, "band rows [%d,%d) need source rows [%d,%d), got [%d,%d)", r0, r1, need0, need1, s0, s1);
+
+    ResizeArgs ra;
+    ra.src = d_src; ra.src_stride = src_stride;
+    ra.sw = w; ra.sh = h; ra.src_row0 = s0; ra.src_row1 = s1;
+    ra.order = order;
+    ra.ow = ow; ra.oh = oh;
+    ra.row_begin = p0; ra.row_end = p1;
+    ra.pl = pl; ra.tx = tx; ra.ty = ty;
+    if ((rc = prof_mark(c))) return rc;
+    rc = launch_color_bicubic(c, ra);
+    if (rc) return rc;
+    if ((rc = prof_mark(c))) return rc;
+
+    CnnArgs ca;
+    ca.y = pl.y; ca.pitch = pl.pitch;
+    ca.W = ow; ca.H = oh;
+    ca.row0 = p0; ca.rows = p1 - p0;
+    ca.out_begin = r0; ca.out_end = r1;
+    ca.out = pl.yout; ca.out_pitch = pl.pitch;
+    rc = run_cnn(c, c->variant, ca);
+    if (rc) return rc;
+    if ((rc = prof_mark(c))) return rc;
+
+    MergeArgs ma;
+    const size_t off = (size_t)(r0 - p0) * pl.pitch;
+    ma.y = pl.yout + off; ma.cr = pl.cr + off; ma.cb = pl.cb + off;
+    ma.pitch = pl.pitch; ma.w = ow; ma.rows = r1 - r0;
+    ma.order = order;
+    ma.dst = d_dst; ma.dst_stride = dst_stride;
+    rc = launch_merge(c, ma);
+    if (rc) return rc;
+    return prof_mark(c);
+}
+
+static int check_guard(Ctx* c) {
+    if (c->h_guard && *c->h_guard != 0) {
+        int v = *c->h_guard;
+        *c->h_guard = 0;
+        return fail(c, SRCNN_E_KERNEL, "device-side pipeline watchdog tripped (code %d)", v);
+    }
+    return SRCNN_OK;
+}
+
+}  // namespace srcnn
+
+using namespace srcnn;
+
+#define ENTER(ctx)                                                                       \
+    if (!(ctx)) return SRCNN_E_ARG;                                                      \
+    do {                                                                                 \
+        cudaError_t e__ = cudaSetDevice((ctx)->device);                                  \
+        if (e__ != cudaSuccess) return fail((ctx), SRCNN_E_CUDA, "cudaSetDevice(%d): %s", (ctx)->device, cudaGetErrorString(e__)); \
+    } while (0)
+
+extern "C" {
+
+int srcnn_abi_version(void) { return SRCNN_B200_ABI_VERSION; }
+
+const char* srcnn_strerror(int s) {
+    switch (s) {
+        case SRCNN_OK: return "ok";
+        case SRCNN_E_RATIO: return "image scale error: ratio too small";
+        case SRCNN_E_ARG: return "invalid argument";
+        case SRCNN_E_NODEVICE: return "no usable CUDA device (sm_100 required; there is no CPU fallback)";
+        case SRCNN_E_CUDA: return "CUDA error";
+        case SRCNN_E_NOMEM: return "out of device or pinned memory";
+        case SRCNN_E_KERNEL: return "device-side guard tripped";
+        default: return "unknown status";
+    }
+}
+
+int srcnn_create(srcnn_ctx** out, int device, int variant) {
+    if (!out) return SRCNN_E_ARG;
+    *out = nullptr;
+    if (variant != SRCNN_VARIANT_TC && variant != SRCNN_VARIANT_FP32) return SRCNN_E_ARG;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) {
+        cudaGetLastError();
+        return SRCNN_E_NODEVICE;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SRCNN_E_NODEVICE;
+    if (prop.major != 10) return SRCNN_E_NODEVICE;  // the only code in this library is sm_100a SASS
+    if (cudaSetDevice(device) != cudaSuccess) return SRCNN_E_NODEVICE;
+    srcnn_ctx* c = new (std::nothrow) srcnn_ctx();
+    if (!c) return SRCNN_E_NOMEM;
+    c->device = device;
+    c->variant = variant;
+    c->sm_count = prop.multiProcessorCount;
+    c->cc_major = prop.major;
+    c->cc_minor = prop.minor;
+    auto bail = [&](int rc) { srcnn_destroy(c); return rc; };
+    if (cudaStreamCreateWithFlags(&c->own, cudaStreamNonBlocking) != cudaSuccess) return bail(SRCNN_E_CUDA);
+    c->stream = c->own;
+    c->own_stream = true;
+    if (srcnn_weights_blob_size != sizeof(float) * kNumParams) return bail(SRCNN_E_ARG);
+    if (cudaMalloc(&c->d_params, sizeof(float) * kNumParams) != cudaSuccess) return bail(SRCNN_E_NOMEM);
+    if (cudaMemcpy(c->d_params, srcnn_weights_blob, sizeof(float) * kNumParams, cudaMemcpyHostToDevice) != cudaSuccess) return bail(SRCNN_E_CUDA);
+    if (cudaHostAlloc((void**)&c->h_guard, sizeof(int), cudaHostAllocMapped) != cudaSuccess) return bail(SRCNN_E_NOMEM);
+    *c->h_guard = 0;
+    if (cudaHostGetDevicePointer((void**)&c->d_guard, c->h_guard, 0) != cudaSuccess) return bail(SRCNN_E_CUDA);
+    int rc = tc_prepare_weights(c, (const float*)srcnn_weights_blob);
+    if (rc) return bail(rc);
+    *out = c;
+    return SRCNN_OK;
+}
+
+int srcnn_destroy(srcnn_ctx* c) {
+    if (!c) return SRCNN_E_ARG;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    tc_release(c);
+    for (auto& t : c->taps) {
+        if (t.d_ofs) cudaFree(t.d_ofs);
+        if (t.d_coef) cudaFree(t.d_coef);
+    }
+    for (DevBuf* b : {&c->plane_buf, &c->act2_buf, &c->src_buf, &c->dst_buf, &c->work_buf})
+        if (b->p) cudaFree(b->p);
+    for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+    if (c->h_work) cudaFreeHost(c->h_work);
+    if (c->d_params) cudaFree(c->d_params);
+    if (c->h_guard) cudaFreeHost(c->h_guard);
+    if (c->own) cudaStreamDestroy(c->own);
+    cudaGetLastError();
+    delete c;
+    return SRCNN_OK;
+}
+
+const char* srcnn_last_error(srcnn_ctx* c) { return c ? c->err : "null context"; }
+
+int srcnn_set_variant(srcnn_ctx* c, int variant) {
+    if (!c || (variant != SRCNN_VARIANT_TC && variant != SRCNN_VARIANT_FP32)) return SRCNN_E_ARG;
+    c->variant = variant;
+    return SRCNN_OK;
+}
+int srcnn_get_variant(srcnn_ctx* c) { return c ? c->variant : SRCNN_E_ARG; }
+
+int srcnn_set_stream(srcnn_ctx* c, void* s) {
+    ENTER(c);
+    SRCNN_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (s) { c->stream = (cudaStream_t)s; c->own_stream = false; }
+    else { c->stream = c->own; c->own_stream = true; }
+    return SRCNN_OK;
+}
+void* srcnn_get_stream(srcnn_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int srcnn_sync(srcnn_ctx* c) {
+    ENTER(c);
+    SRCNN_CUDA(c, cudaStreamSynchronize(c->stream));
+    return check_guard(c);
+}
+
+long long srcnn_launch_count(srcnn_ctx* c) { return c ? c->launches : -1; }
+int srcnn_device_sm_count(srcnn_ctx* c) { return c ? c->sm_count : SRCNN_E_ARG; }
+
+int srcnn_profile_enable(srcnn_ctx* c, int on) {
+    ENTER(c);
+    SRCNN_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->profiling = on != 0;
+    c->ev_used = 0;
+    return SRCNN_OK;
+}
+
+// Sums the device time of the three stages over every whole-path call since the last read:
+// ms[0] colour+bicubic, ms[1] fused SRCNN, ms[2] merge+colour-back; *calls = number of calls.
+int srcnn_profile_read(srcnn_ctx* c, double* ms, int* calls) {
+    ENTER(c);
+    if (!ms || !calls) return fail(c, SRCNN_E_ARG, "null pointer");
+    SRCNN_CUDA(c, cudaStreamSynchronize(c->stream));
+    ms[0] = ms[1] = ms[2] = 0.0;
+    const size_t n = c->ev_used / 4;
+    for (size_t i = 0; i < n; i++)
+        for (int k = 0; k < 3; k++) {
+            float t = 0.f;
+            SRCNN_CUDA(c, cudaEventElapsedTime(&t, c->ev_pool[4 * i + k], c->ev_pool[4 * i + k + 1]));
+            ms[k] += t;
+        }
+    *calls = (int)n;
+    c->ev_used = 0;
+    return SRCNN_OK;
+}
+
+int srcnn_out_dims(int w, int h, float scale, int* ow, int* oh) {
+    if (!ow || !oh || w <= 0 || h <= 0) return SRCNN_E_ARG;
+    if (!(((float)w * scale) > 0.f) || !(((float)h * scale) > 0.f)) return SRCNN_E_RATIO;
+    *ow = scaled_dim(w, scale);
+    *oh = scaled_dim(h, scale);
+    return (*ow > 0 && *oh > 0) ? SRCNN_OK : SRCNN_E_RATIO;
+}
+
+int srcnn_host_alloc(void** p, size_t bytes) {
+    if (!p) return SRCNN_E_ARG;
+    cudaError_t e = cudaHostAlloc(p, bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) { cudaGetLastError(); *p = nullptr; return SRCNN_E_NOMEM; }
+    return SRCNN_OK;
+}
+int srcnn_host_free(void* p) {
+    if (!p) return SRCNN_OK;
+    return cudaFreeHost(p) == cudaSuccess ? SRCNN_OK : SRCNN_E_CUDA;
+}
+
+int srcnn_process_device(srcnn_ctx* c, const uint8_t* d_src, int w, int h, size_t src_stride, int order, float scale,
+                         uint8_t* d_dst, size_t dst_stride) {
+    ENTER(c);
+    int ow, oh;
+    int rc = check_image(c, d_src, w, h, src_stride, order, scale, d_dst, dst_stride, &ow, &oh);
+    if (rc) return rc;
+    return process_rows(c, d_src, w, h, src_stride, 0, h, order, scale, ow, oh, 0, oh, d_dst, dst_stride);
+}
+
+int srcnn_process_batch_device(srcnn_ctx* c, const uint8_t* d_src, int n, int w, int h, size_t src_stride,
+                               size_t src_frame_stride, int order, float scale, uint8_t* d_dst, size_t dst_stride,
+                               size_t dst_frame_stride) {
+    ENTER(c);
+    if (n < 0) return fail(c, SRCNN_E_ARG, "negative frame count");
+    if (n == 0) return SRCNN_OK;
+    int ow, oh;
+    int rc = check_image(c, d_src, w, h, src_stride, order, scale, d_dst, dst_stride, &ow, &oh);
+    if (rc) return rc;
+    if (n > 1 && (src_frame_stride < src_stride * (size_t)h || dst_frame_stride < dst_stride * (size_t)oh))
+        return fail(c, SRCNN_E_ARG, "frame stride smaller than one frame");
+    for (int f = 0; f < n; f++) {
+        rc = process_rows(c, d_src + (size_t)f * src_frame_stride, w, h, src_stride, 0, h, order, scale, ow, oh, 0, oh,
+                          d_dst + (size_t)f * dst_frame_stride, dst_stride);
+        if (rc) return rc;
+    }
+    return SRCNN_OK;
+}
+
+int srcnn_process_batch_host(srcnn_ctx* c, const uint8_t* src, int n, int w, int h, size_t src_stride,
+                             size_t src_frame_stride, int order, float scale, uint8_t* dst, size_t dst_stride,
+                             size_t dst_frame_stride) {
+    ENTER(c);
+    if (n < 0) return fail(c, SRCNN_E_ARG, "negative frame count");
+    if (n == 0) return SRCNN_OK;
+    int ow, oh;
+    int rc = check_image(c, src, w, h, src_stride, order, scale, dst, dst_stride, &ow, &oh);
+    if (rc) return rc;
+    if (n > 1 && (src_frame_stride < src_stride * (size_t)h || dst_frame_stride < dst_stride * (size_t)oh))
+        return fail(c, SRCNN_E_ARG, "frame stride smaller than one frame");
+    // device staging: tight rows, 256-byte aligned frames
+    const size_t s_row = align_up((size_t)w * 3, 4), d_row = align_up((size_t)ow * 3, 4);
+    const size_t s_frame = align_up(s_row * h, 256), d_frame = align_up(d_row * oh, 256);
+    // frames in flight are bounded so staging stays modest (<= ~1 GiB of output)
+    int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n, ((size_t)1 << 30) / d_frame));
+    rc = ensure(c, c->src_buf, s_frame * chunk);
+    if (rc) return rc;
+    rc = ensure(c, c->dst_buf, d_frame * chunk);
+    if (rc) return rc;
+    uint8_t* ds = (uint8_t*)c->src_buf.p;
+    uint8_t* dd = (uint8_t*)c->dst_buf.p;
+    for (int f0 = 0; f0 < n; f0 += chunk) {
+        const int m = std::min(chunk, n - f0);
+        for (int f = 0; f < m; f++)
+            SRCNN_CUDA(c, cudaMemcpy2DAsync(ds + f * s_frame, s_row, src + (size_t)(f0 + f) * src_frame_stride, src_stride,
+                                            (size_t)w * 3, h, cudaMemcpyHostToDevice, c->stream));
+        for (int f = 0; f < m; f++) {
+            rc = process_rows(c, ds + f * s_frame, w, h, s_row, 0, h, order, scale, ow, oh, 0, oh, dd + f * d_frame, d_row);
+            if (rc) return rc;
+            SRCNN_CUDA(c, cudaMemcpy2DAsync(dst + (size_t)(f0 + f) * dst_frame_stride, dst_stride, dd + f * d_frame, d_row,
+                                            (size_t)ow * 3, oh, cudaMemcpyDeviceToHost, c->stream));
+        }
+        SRCNN_CUDA(c, cudaStreamSynchronize(c->stream));
+        rc = check_guard(c);
+        if (rc) return rc;
+    }
+    return SRCNN_OK;
+}
+
+int srcnn_process_host(srcnn_ctx* c, const uint8_t* src, int w, int h, size_t src_stride, int order, float scale,
+                       uint8_t* dst, size_t dst_stride) {
+    return srcnn_process_batch_host(c, src, 1, w, h, src_stride, 0, order, scale, dst, dst_stride, 0);
+}
+
+int srcnn_band_src_rows(int h, float scale, int r0, int r1, int* s0, int* s1) {
+    if (!s0 || !s1 || h <= 0) return SRCNN_E_ARG;
+    if (!(((float)h * scale) > 0.f)) return SRCNN_E_RATIO;
+    const int oh = scaled_dim(h, scale);
+    if (oh <= 0) return SRCNN_E_RATIO;
+    if (r0 < 0 || r1 > oh || r0 >= r1) return SRCNN_E_ARG;
+    const int p0 = std::max(r0 - 6, 0), p1 = std::min(r1 + 6, oh);
+    std::vector<int> ofs(oh);
+    std::vector<short4> coef(oh);
+    build_cubic_taps(h, oh, ofs.data(), coef.data());
+    *s0 = std::min(std::max(ofs[p0] - 1, 0), h - 1);
+    *s1 = std::min(std::max(ofs[p1 - 1] + 2, 0), h - 1) + 1;
+    return SRCNN_OK;
+}
+
+int srcnn_process_band_device(srcnn_ctx* c, const uint8_t* d_src, int w, int h, size_t src_stride, int s0, int s1,
+                              int order, float scale, int r0, int r1, uint8_t* d_dst, size_t dst_stride) {
+    ENTER(c);
+    int ow, oh;
+    int rc = check_image(c, d_src, w, h, src_stride, order, scale, d_dst, dst_stride, &ow, &oh);
+    if (rc) return rc;
+    if (r0 < 0 || r1 > oh || r0 >= r1) return fail(c, SRCNN_E_ARG, "bad output band [%d,%d) of %d rows", r0, r1, oh);
+    if (s0 < 0 || s1 > h || s0 >= s1) return fail(c, SRCNN_E_ARG, "bad source band [%d,%d) of %d rows", s0, s1, h);
+    return process_rows(c, d_src, w, h, src_stride, s0, s1, order, scale, ow, oh, r0, r1, d_dst, dst_stride);
+}
+
+int srcnn_stage_color_bicubic_device(srcnn_ctx* c, const uint8_t* d_src, int w, int h, size_t src_stride, int order,
+                                     float scale, uint8_t* d_y, uint8_t* d_cr, uint8_t* d_cb, size_t plane_pitch) {
+    ENTER(c);
+    if (!d_src || !d_y || !d_cr || !d_cb) return fail(c, SRCNN_E_ARG, "null pointer");
+    if (w <= 0 || h <= 0 || src_stride < (size_t)w * 3) return fail(c, SRCNN_E_ARG, "bad source geometry");
+    if (!(((float)w * scale) > 0.f) || !(((float)h * scale) > 0.f)) return fail(c, SRCNN_E_RATIO, "ratio too small");
+    const int ow = scaled_dim(w, scale), oh = scaled_dim(h, scale);
+    if (ow <= 0 || oh <= 0) return fail(c, SRCNN_E_RATIO, "ratio too small");
+    if (plane_pitch < align_up((size_t)ow, 4) || (plane_pitch & 3) || (((uintptr_t)d_y | (uintptr_t)d_cr | (uintptr_t)d_cb) & 3))
+        return fail(c, SRCNN_E_ARG, "planes must be 4-byte aligned with pitch a multiple of 4 and >= ow rounded up to 4");
+    TapTable *tx, *ty;
+    int rc = get_taps(c, w, ow, &tx);
+    if (rc) return rc;
+    rc = get_taps(c, h, oh, &ty);
+    if (rc) return rc;
+    ResizeArgs ra;
+    ra.src = d_src; ra.src_stride = src_stride;
+    ra.sw = w; ra.sh = h; ra.src_row0 = 0; ra.src_row1 = h;
+    ra.order = order; ra.ow = ow; ra.oh = oh;
+    ra.row_begin = 0; ra.row_end = oh;
+    ra.pl.y = d_y; ra.pl.cr = d_cr; ra.pl.cb = d_cb; ra.pl.yout = nullptr;
+    ra.pl.pitch = plane_pitch; ra.pl.row0 = 0; ra.pl.rows = oh;
+    ra.tx = tx; ra.ty = ty;
+    return launch_color_bicubic(c, ra);
+}
+
+int srcnn_stage_cnn_device(srcnn_ctx* c, int variant, const uint8_t* d_y, int w, int h, size_t pitch, uint8_t* d_out,
+                           size_t out_pitch) {
+    ENTER(c);
+    if (!d_y || !d_out) return fail(c, SRCNN_E_ARG, "null pointer");
+    if (w <= 0 || h <= 0 || pitch < (size_t)w || out_pitch < (size_t)w) return fail(c, SRCNN_E_ARG, "bad plane geometry");
+    CnnArgs ca;
+    ca.y = d_y; ca.pitch = pitch; ca.W = w; ca.H = h;
+    ca.row0 = 0; ca.rows = h; ca.out_begin = 0; ca.out_end = h;
+    ca.out = d_out; ca.out_pitch = out_pitch;
+    return run_cnn(c, variant, ca);
+}
+
+int srcnn_stage_conv99x11_fp32_device(srcnn_ctx* c, const uint8_t* d_y, int w, int h, size_t pitch, float* d_act2) {
+    ENTER(c);
+    if (!d_y || !d_act2) return fail(c, SRCNN_E_ARG, "null pointer");
+    if (w <= 0 || h <= 0 || pitch < (size_t)w) return fail(c, SRCNN_E_ARG, "bad plane geometry");
+    CnnArgs ca;
+    ca.y = d_y; ca.pitch = pitch; ca.W = w; ca.H = h;
+    ca.row0 = 0; ca.rows = h; ca.out_begin = 0; ca.out_end = h;
+    ca.out = nullptr; ca.out_pitch = 0;
+    return launch_cnn_fp32(c, ca, d_act2);
+}
+
+int srcnn_stage_merge_device(srcnn_ctx* c, const uint8_t* d_y, const uint8_t* d_cr, const uint8_t* d_cb, int w, int h,
+                             size_t plane_pitch, int order, uint8_t* d_dst, size_t dst_stride) {
+    ENTER(c);
+    if (!d_y || !d_cr || !d_cb || !d_dst) return fail(c, SRCNN_E_ARG, "null pointer");
+    if (w <= 0 || h <= 0 || dst_stride < (size_t)w * 3) return fail(c, SRCNN_E_ARG, "bad geometry");
+    if (plane_pitch < align_up((size_t)w, 4) || (plane_pitch & 3) || (((uintptr_t)d_y | (uintptr_t)d_cr | (uintptr_t)d_cb) & 3))
+        return fail(c, SRCNN_E_ARG, "planes must be 4-byte aligned with pitch a multiple of 4 and >= w rounded up to 4");
+    MergeArgs ma;
+    ma.y = d_y; ma.cr = d_cr; ma.cb = d_cb; ma.pitch = plane_pitch;
+    ma.w = w; ma.rows = h; ma.order = order; ma.dst = d_dst; ma.dst_stride = dst_stride;
+    return launch_merge(c, ma);
+}
+
+}  // extern "C"

@@ -1,0 +1,358 @@
+// color_bicubic.cu -- kernels A and C of the hot path (HBM-bound stages).
+//
+//   K-A  colour + split + bicubic:  BGR8 HWC  ->  Y, Cr, Cb u8 planes of the upscaled size.
+//        Replaces cvtColor(BGR2YCrCb) src/srcnn.cpp:509, split :540 and the three
+//        resize(..., CV_INTER_CUBIC) calls :570-583 of the reference with ONE pass over the source.
+//   K-C  merge + colour back:       Y', Cr, Cb planes -> BGR8 HWC.
+//        Replaces `pImg[0] = pImgConv3; merge` src/srcnn.cpp:637-639 and cvtColor(YCrCb2BGR) :657.
+//
+// Arithmetic is OpenCV's 8-bit path restated from its published algorithm:
+// 14-bit fixed-point BT.601 colour; Keys cubic A=-0.75 with 11-bit integer taps, integer horizontal
+// pass, float vertical pass `H0*b0 + (H1*b1 + (H2*b2 + H3*b3))` with separate multiplies and adds
+// (hence __fmul_rn/__fadd_rn: no FMA contraction), round-half-even, and the integer form on the
+// last (ow mod 8) columns.  Results are bit-identical to the oracle (tests/test_stage_parity.py).
+//
+// Algorithmic HBM bytes per output pixel: 3/s^2 (BGR read) + 3 (planes written); K-C: 3 + 3.
+#include <cmath>
+#include <cstdarg>
+
+#include "common.h"
+
+namespace srcnn {
+
+// ------------------------------------------------------------------------------------------------
+// Host: tap tables.  Same float32/double sequence as cv::resize's table builder; nvcc host flags in
+// the Makefile forbid FMA contraction.
+// ------------------------------------------------------------------------------------------------
+void build_cubic_taps(int src, int dst, int* ofs, short4* coef) {
+    const float A = -0.75f;
+    const double inv = (double)dst / (double)src;
+    const double sc = 1.0 / inv;
+    for (int d = 0; d < dst; d++) {
+        float f = (float)((d + 0.5) * sc - 0.5);
+        int s = (int)floorf(f);
+        float x = f - (float)s;
+        float x1 = x + 1.f;
+        float c0 = ((A * x1 - 5 * A) * x1 + 8 * A) * x1 - 4 * A;
+        float c1 = ((A + 2) * x - (A + 3)) * x * x + 1;
+        float y = 1.f - x;
+        float c2 = ((A + 2) * y - (A + 3)) * y * y + 1;
+        float c3 = 1.f - c0 - c1 - c2;
+        float cf[4] = {c0, c1, c2, c3};
+        short q[4];
+        for (int k = 0; k < 4; k++) {
+            long r = lrintf(cf[k] * 2048.f);
+            r = r > 32767 ? 32767 : (r < -32768 ? -32768 : r);
+            q[k] = (short)r;
+        }
+        ofs[d] = s;
+        coef[d] = make_short4(q[0], q[1], q[2], q[3]);
+    }
+}
+
+int get_taps(Ctx* c, int src, int dst, TapTable** out) {
+    TapTable* victim = &c->taps[0];
+    for (auto& t : c->taps) {
+        if (t.src == src && t.dst == dst && t.d_ofs) {
+            t.stamp = ++c->tap_clock;
+            *out = &t;
+            return SRCNN_OK;
+        }
+        if (t.stamp < victim->stamp) victim = &t;
+    }
+    TapTable& t = *victim;
+    if (t.d_ofs) {  // evict: in-flight kernels may still read it
+        SRCNN_CUDA(c, cudaStreamSynchronize(c->stream));
+        cudaFree(t.d_ofs);
+        cudaFree(t.d_coef);
+        t.d_ofs = nullptr;
+        t.d_coef = nullptr;
+    }
+    t.src = src;
+    t.dst = dst;
+    t.h_ofs.resize(dst);
+    t.h_coef.resize(dst);
+    build_cubic_taps(src, dst, t.h_ofs.data(), t.h_coef.data());
+    SRCNN_CUDA(c, cudaMalloc(&t.d_ofs, sizeof(int) * (size_t)dst));
+    SRCNN_CUDA(c, cudaMalloc(&t.d_coef, sizeof(short4) * (size_t)dst));
+    // pageable source: the runtime stages it before returning, so the vectors may be reused freely
+    SRCNN_CUDA(c, cudaMemcpyAsync(t.d_ofs, t.h_ofs.data(), sizeof(int) * (size_t)dst, cudaMemcpyHostToDevice, c->stream));
+    SRCNN_CUDA(c, cudaMemcpyAsync(t.d_coef, t.h_coef.data(), sizeof(short4) * (size_t)dst, cudaMemcpyHostToDevice, c->stream));
+    t.stamp = ++c->tap_clock;
+    *out = &t;
+    return SRCNN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
+
+// BGR -> Y,Cr,Cb  (OpenCV RGB2YCrCb_i<uchar>: yuv_shift 14)
+__device__ __forceinline__ void bgr_to_ycc(int B, int G, int R, int& Y, int& Cr, int& Cb) {
+    Y = (1868 * B + 9617 * G + 4899 * R + 8192) >> 14;
+    Cr = clampi(((R - Y) * 11682 + (128 << 14) + 8192) >> 14, 0, 255);
+    Cb = clampi(((B - Y) * 9241 + (128 << 14) + 8192) >> 14, 0, 255);
+}
+
+// Vertical cubic pass on four horizontal sums.  `fpath`: column belongs to cv::resize's 8-lane float
+// body (dx < (ow/8)*8), else to its integer scalar tail.
+__device__ __forceinline__ int vertical_tap(int h0, int h1, int h2, int h3, short4 c, bool fpath) {
+    int r;
+    if (fpath) {
+        const float s = 1.0f / 4194304.0f;  // 2^-22, exact
+        const float b0 = __fmul_rn((float)c.x, s), b1 = __fmul_rn((float)c.y, s);
+        const float b2 = __fmul_rn((float)c.z, s), b3 = __fmul_rn((float)c.w, s);
+        float v = __fmul_rn((float)h3, b3);
+        v = __fadd_rn(__fmul_rn((float)h2, b2), v);
+        v = __fadd_rn(__fmul_rn((float)h1, b1), v);
+        v = __fadd_rn(__fmul_rn((float)h0, b0), v);
+        r = __float2int_rn(v);
+    } else {
+        r = (h0 * (int)c.x + h1 * (int)c.y + h2 * (int)c.z + h3 * (int)c.w + (1 << 21)) >> 22;
+    }
+    return clampi(r, 0, 255);
+}
+
+struct ResizeDev {
+    const uint8_t* src;
+    size_t src_stride;
+    int sw, sh, src_row0;
+    int swapRB;
+    int ow, oh;
+    int row_begin, row_end;
+    uint8_t* y;
+    uint8_t* cr;
+    uint8_t* cb;
+    size_t pitch;
+    int plane_row0;
+    const int* xofs;
+    const short4* xcoef;
+    const int* yofs;
+    const short4* ycoef;
+    int simd_w;
+};
+
+// ------------------------------------------------------------------------------------------------
+// K-A, direct form: one thread per output pixel, everything from global memory.  Used for any
+// geometry the tiled kernel's shared-memory footprint cannot hold (strong down-scales) and as the
+// in-library cross-check of the tiled kernel.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_color_bicubic_direct(ResizeDev p) {
+    const int dx = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int dy = p.row_begin + blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (dx >= p.ow || dy >= p.row_end) return;
+    const int sx = p.xofs[dx], sy = p.yofs[dy];
+    const short4 cx = p.xcoef[dx], cy = p.ycoef[dy];
+    const int cxs[4] = {cx.x, cx.y, cx.z, cx.w};
+    int hY[4], hCr[4], hCb[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int gy = clampi(sy - 1 + r, 0, p.sh - 1) - p.src_row0;
+        const uint8_t* row = p.src + (size_t)gy * p.src_stride;
+        int aY = 0, aCr = 0, aCb = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int gx = clampi(sx - 1 + k, 0, p.sw - 1);
+            int c0 = row[3 * gx], c1 = row[3 * gx + 1], c2 = row[3 * gx + 2];
+            int B = p.swapRB ? c2 : c0, R = p.swapRB ? c0 : c2;
+            int Y, Cr, Cb;
+            bgr_to_ycc(B, c1, R, Y, Cr, Cb);
+            aY += Y * cxs[k];
+            aCr += Cr * cxs[k];
+            aCb += Cb * cxs[k];
+        }
+        hY[r] = aY; hCr[r] = aCr; hCb[r] = aCb;
+    }
+    const bool fpath = dx < p.simd_w;
+    const size_t o = (size_t)(dy - p.plane_row0) * p.pitch + dx;
+    p.y[o] = (uint8_t)vertical_tap(hY[0], hY[1], hY[2], hY[3], cy, fpath);
+    p.cr[o] = (uint8_t)vertical_tap(hCr[0], hCr[1], hCr[2], hCr[3], cy, fpath);
+    p.cb[o] = (uint8_t)vertical_tap(hCb[0], hCb[1], hCb[2], hCb[3], cy, fpath);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K-A, tiled form (the fast path for up-scaling).  One CTA produces a TW x TH tile of all three
+// planes: (1) the source footprint is colour-converted ONCE into shared memory (three u8 planes,
+// replicate border applied at load), (2) the integer horizontal pass runs once per footprint row,
+// (3) the vertical pass reads four shared-memory sums per sample and writes 4 pixels per store.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTW = 64, kTH = 32;       // output tile
+constexpr int kMaxSC = 72, kMaxSR = 40; // footprint capacity (source cols / rows incl. the 3-tap apron)
+
+__global__ void __launch_bounds__(256) k_color_bicubic_tiled(ResizeDev p) {
+    __shared__ uint8_t sP[3][kMaxSR][kMaxSC];
+    __shared__ int sH[3][kMaxSR][kTW];
+
+    const int dx0 = blockIdx.x * kTW;
+    const int dy0 = p.row_begin + blockIdx.y * kTH;
+    const int dx1 = min(dx0 + kTW, p.ow), dy1 = min(dy0 + kTH, p.row_end);
+    const int sx_lo = p.xofs[dx0] - 1, sx_hi = p.xofs[dx1 - 1] + 2;
+    const int sy_lo = p.yofs[dy0] - 1, sy_hi = p.yofs[dy1 - 1] + 2;
+    const int nsc = sx_hi - sx_lo + 1, nsr = sy_hi - sy_lo + 1;
+    const int tid = threadIdx.x;
+
+    // (1) colour-convert the footprint
+    for (int i = tid; i < nsr * nsc; i += 256) {
+        const int r = i / nsc, c = i - r * nsc;
+        const int gy = clampi(sy_lo + r, 0, p.sh - 1) - p.src_row0;
+        const int gx = clampi(sx_lo + c, 0, p.sw - 1);
+        const uint8_t* px = p.src + (size_t)gy * p.src_stride + 3 * (size_t)gx;
+        int c0 = px[0], c1 = px[1], c2 = px[2];
+        int B = p.swapRB ? c2 : c0, R = p.swapRB ? c0 : c2;
+        int Y, Cr, Cb;
+        bgr_to_ycc(B, c1, R, Y, Cr, Cb);
+        sP[0][r][c] = (uint8_t)Y;
+        sP[1][r][c] = (uint8_t)Cr;
+        sP[2][r][c] = (uint8_t)Cb;
+    }
+    __syncthreads();
+
+    // (2) horizontal pass: thread owns one output column (and a quarter of the footprint rows)
+    {
+        const int col = tid & (kTW - 1);
+        const int dx = dx0 + col;
+        if (dx < dx1) {
+            const int s = p.xofs[dx] - 1 - sx_lo;
+            const short4 cx = p.xcoef[dx];
+            for (int r = tid >> 6; r < nsr; r += 256 / kTW) {
+#pragma unroll
+                for (int pl = 0; pl < 3; pl++) {
+                    const uint8_t* q = &sP[pl][r][s];
+                    sH[pl][r][col] = (int)q[0] * cx.x + (int)q[1] * cx.y + (int)q[2] * cx.z + (int)q[3] * cx.w;
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // (3) vertical pass, 4 consecutive columns per thread
+    const int qcols = kTW / 4;
+    for (int i = tid; i < 3 * kTH * qcols; i += 256) {
+        const int pl = i / (kTH * qcols);
+        const int rem = i - pl * (kTH * qcols);
+        const int ty = rem / qcols, q = rem - ty * qcols;
+        const int dy = dy0 + ty;
+        if (dy >= dy1) continue;
+        const int col = q * 4, dx = dx0 + col;
+        if (dx >= dx1) continue;
+        const int sr = p.yofs[dy] - 1 - sy_lo;
+        const short4 cy = p.ycoef[dy];
+        uint8_t* out = (pl == 0 ? p.y : (pl == 1 ? p.cr : p.cb)) + (size_t)(dy - p.plane_row0) * p.pitch + dx;
+        uint32_t packed = 0;
+        int v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const bool fpath = (dx + j) < p.simd_w;
+            v[j] = vertical_tap(sH[pl][sr][col + j], sH[pl][sr + 1][col + j], sH[pl][sr + 2][col + j],
+                                sH[pl][sr + 3][col + j], cy, fpath);
+            packed |= (uint32_t)v[j] << (8 * j);
+        }
+        if (dx + 3 < dx1) {
+            *reinterpret_cast<uint32_t*>(out) = packed;  // pitch and dx are multiples of 4
+        } else {
+            for (int j = 0; j < 4 && dx + j < dx1; j++) out[j] = (uint8_t)v[j];
+        }
+    }
+}
+
+int launch_color_bicubic(Ctx* c, const ResizeArgs& a) {
+    ResizeDev p;
+    p.src = a.src;
+    p.src_stride = a.src_stride;
+    p.sw = a.sw; p.sh = a.sh; p.src_row0 = a.src_row0;
+    p.swapRB = a.order == SRCNN_ORDER_RGB;
+    p.ow = a.ow; p.oh = a.oh;
+    p.row_begin = a.row_begin; p.row_end = a.row_end;
+    p.y = a.pl.y; p.cr = a.pl.cr; p.cb = a.pl.cb;
+    p.pitch = a.pl.pitch;
+    p.plane_row0 = a.pl.row0;
+    p.xofs = a.tx->d_ofs; p.xcoef = a.tx->d_coef;
+    p.yofs = a.ty->d_ofs; p.ycoef = a.ty->d_coef;
+    p.simd_w = (a.ow / 8) * 8;
+    const int rows = a.row_end - a.row_begin;
+    if (rows <= 0) return SRCNN_OK;
+
+    // does every tile's source footprint fit the tiled kernel's shared memory?
+    bool fits = true;
+    for (int dx0 = 0; dx0 < a.ow && fits; dx0 += kTW) {
+        int dx1 = std::min(dx0 + kTW, a.ow);
+        if (a.tx->h_ofs[dx1 - 1] - a.tx->h_ofs[dx0] + 4 > kMaxSC) fits = false;
+    }
+    for (int dy0 = a.row_begin; dy0 < a.row_end && fits; dy0 += kTH) {
+        int dy1 = std::min(dy0 + kTH, a.row_end);
+        if (a.ty->h_ofs[dy1 - 1] - a.ty->h_ofs[dy0] + 4 > kMaxSR) fits = false;
+    }
+    if (fits) {
+        dim3 grid((a.ow + kTW - 1) / kTW, (rows + kTH - 1) / kTH);
+        k_color_bicubic_tiled<<<grid, 256, 0, c->stream>>>(p);
+    } else {
+        dim3 grid((a.ow + 31) / 32, (rows + 7) / 8);
+        k_color_bicubic_direct<<<grid, 256, 0, c->stream>>>(p);
+    }
+    c->launches++;
+    SRCNN_CUDA(c, cudaGetLastError());
+    return SRCNN_OK;
+}
+
+// test hook: force the direct form (exported through the C ABI as a stage option is overkill; the
+// tiled/direct agreement is covered by running geometries on both sides of the footprint limit)
+
+// ------------------------------------------------------------------------------------------------
+// K-C: merge + YCrCb -> BGR.  4 pixels per thread: three aligned 32-bit plane loads, 12 output bytes.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ycc_to_bgr(int Y, int Cr, int Cb, int& B, int& G, int& R) {
+    const int cr = Cr - 128, cb = Cb - 128;
+    B = clampi(Y + ((cb * 29049 + 8192) >> 14), 0, 255);
+    G = clampi(Y + ((cb * -5636 + cr * -11698 + 8192) >> 14), 0, 255);
+    R = clampi(Y + ((cr * 22987 + 8192) >> 14), 0, 255);
+}
+
+__global__ void __launch_bounds__(256) k_merge_ycc2bgr(const uint8_t* __restrict__ y, const uint8_t* __restrict__ cr,
+                                                       const uint8_t* __restrict__ cb, size_t pitch, int w, int rows,
+                                                       int swapRB, uint8_t* __restrict__ dst, size_t dst_stride,
+                                                       int dst_aligned, int blocks_per_row) {
+    // 1-D grid (rows can exceed the 65535 limit of gridDim.y): blocks_per_row blocks per image row
+    const int row = blockIdx.x / blocks_per_row;
+    const int q = (blockIdx.x - row * blocks_per_row) * blockDim.x + threadIdx.x;  // 4-pixel group
+    const int x = q * 4;
+    if (x >= w || row >= rows) return;
+    const size_t o = (size_t)row * pitch + x;
+    const uint32_t vy = *reinterpret_cast<const uint32_t*>(y + o);
+    const uint32_t vr = *reinterpret_cast<const uint32_t*>(cr + o);
+    const uint32_t vb = *reinterpret_cast<const uint32_t*>(cb + o);
+    uint8_t px[12];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        int B, G, R;
+        ycc_to_bgr((vy >> (8 * j)) & 255, (vr >> (8 * j)) & 255, (vb >> (8 * j)) & 255, B, G, R);
+        px[3 * j] = (uint8_t)(swapRB ? R : B);
+        px[3 * j + 1] = (uint8_t)G;
+        px[3 * j + 2] = (uint8_t)(swapRB ? B : R);
+    }
+    uint8_t* d = dst + (size_t)row * dst_stride + 3 * (size_t)x;
+    if (dst_aligned && x + 3 < w) {
+        uint32_t* d32 = reinterpret_cast<uint32_t*>(d);
+        d32[0] = px[0] | (px[1] << 8) | (px[2] << 16) | ((uint32_t)px[3] << 24);
+        d32[1] = px[4] | (px[5] << 8) | (px[6] << 16) | ((uint32_t)px[7] << 24);
+        d32[2] = px[8] | (px[9] << 8) | (px[10] << 16) | ((uint32_t)px[11] << 24);
+    } else {
+        const int n = min(4, w - x) * 3;
+        for (int j = 0; j < n; j++) d[j] = px[j];
+    }
+}
+
+int launch_merge(Ctx* c, const MergeArgs& a) {
+    if (a.rows <= 0 || a.w <= 0) return SRCNN_OK;
+    const int groups = (a.w + 3) / 4;
+    const int bpr = (groups + 255) / 256;
+    const unsigned grid = (unsigned)bpr * (unsigned)a.rows;
+    const int aligned = (((uintptr_t)a.dst & 3) == 0) && ((a.dst_stride & 3) == 0);
+    k_merge_ycc2bgr<<<grid, 256, 0, c->stream>>>(a.y, a.cr, a.cb, a.pitch, a.w, a.rows,
+                                                 a.order == SRCNN_ORDER_RGB, a.dst, a.dst_stride, aligned, bpr);
+    c->launches++;
+    SRCNN_CUDA(c, cudaGetLastError());
+    return SRCNN_OK;
+}
+
+}  // namespace srcnn

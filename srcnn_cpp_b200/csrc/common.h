@@ -1,0 +1,145 @@
+// common.h -- internal declarations shared by the translation units of libsrcnn_b200.so.
+// Nothing here is part of the C ABI (include/srcnn_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../include/srcnn_b200.h"
+#include "weights.h"
+
+namespace srcnn {
+
+// ---- error plumbing: every CUDA call is checked and turned into a status + message ---------------
+struct Ctx;
+int fail(Ctx* c, int status, const char* fmt, ...);
+
+#define SRCNN_CUDA(ctx, expr)                                                                       \
+    do {                                                                                            \
+        cudaError_t e__ = (expr);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return srcnn::fail((ctx), e__ == cudaErrorMemoryAllocation ? SRCNN_E_NOMEM : SRCNN_E_CUDA, \
+                               "%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); \
+    } while (0)
+
+// ---- a grow-only device buffer --------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+// ---- bicubic tap tables for one (src -> dst) axis pair, resident on the device --------------------
+// ofs[d]  = floor(source coordinate of destination sample d)       (may be -1 .. src-1; taps ofs-1..ofs+2)
+// coef[d] = the four 11-bit fixed-point Keys-cubic taps (A=-0.75), exactly as cv::resize builds them.
+struct TapTable {
+    int src = 0, dst = 0;
+    int* d_ofs = nullptr;
+    short4* d_coef = nullptr;
+    std::vector<int> h_ofs;      // host copies (band planning, footprint bounds)
+    std::vector<short4> h_coef;
+    unsigned long long stamp = 0;
+};
+
+// ---- plane set produced by the colour+bicubic kernel and consumed by the CNN / merge kernels ------
+// Planes are u8, `pitch` bytes per row (multiple of 128), `rows` rows starting at output row `row0`.
+struct Planes {
+    uint8_t* y = nullptr;
+    uint8_t* cr = nullptr;
+    uint8_t* cb = nullptr;
+    uint8_t* yout = nullptr;
+    size_t pitch = 0;
+    int row0 = 0, rows = 0;
+};
+
+struct TcWeights;  // srcnn_tc.cu
+
+struct Ctx {
+    int device = 0;
+    int variant = SRCNN_VARIANT_TC;
+    int sm_count = 0;
+    int cc_major = 0, cc_minor = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaStream_t own = nullptr;
+    long long launches = 0;
+    char err[512] = {0};
+
+    float* d_params = nullptr;       // the 8129 fp32 parameters (FP32 variant reads these)
+    void* d_tc_weights = nullptr;    // packed FP16 operand images for the tcgen05 kernel
+    size_t tc_weights_bytes = 0;
+    int* d_guard = nullptr;          // device-side watchdog flag (mapped pinned)
+    int* h_guard = nullptr;
+
+    DevBuf plane_buf;   // Y, Cr, Cb, Y' planes
+    DevBuf act2_buf;    // FP32 variant: conv2 activations (32 float planes) of one row chunk
+    DevBuf src_buf;     // device copy of a host source image / batch
+    DevBuf dst_buf;     // device copy of the result before D2H
+    DevBuf work_buf;    // TC kernel work list
+    void* h_work = nullptr;          // pinned staging for the work list
+    size_t h_work_cap = 0;
+
+    TapTable taps[8];
+    unsigned long long tap_clock = 0;
+
+    // optional per-stage device timing (srcnn_profile_*): 4 events per process call
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+};
+int prof_mark(Ctx* c);   // records the next event of the pool on c->stream when profiling is on
+
+int ensure(Ctx* c, DevBuf& b, size_t bytes);
+int get_taps(Ctx* c, int src, int dst, TapTable** out);
+void build_cubic_taps(int src, int dst, int* ofs, short4* coef);
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---- kernel launchers (each enqueues on c->stream and bumps c->launches) ---------------------------
+struct ResizeArgs {
+    const uint8_t* src;   // points at source row `src_row0`
+    size_t src_stride;
+    int sw, sh;           // full source image size
+    int src_row0, src_row1;  // source rows present at src: [src_row0, src_row1)
+    int order;
+    int ow, oh;           // full output image size
+    int row_begin, row_end;  // output rows to produce
+    Planes pl;            // destination planes (pl.row0 = output row stored at plane row 0)
+    const TapTable* tx;
+    const TapTable* ty;
+};
+int launch_color_bicubic(Ctx* c, const ResizeArgs& a);
+
+struct MergeArgs {
+    const uint8_t* y;
+    const uint8_t* cr;
+    const uint8_t* cb;
+    size_t pitch;
+    int w, rows;
+    int order;
+    uint8_t* dst;
+    size_t dst_stride;
+};
+int launch_merge(Ctx* c, const MergeArgs& a);
+
+// CNN on a plane band.  y points at plane row 0 which is image row `row0`; the plane holds image rows
+// [row0, row0+rows).  Produces image rows [out_begin, out_end) into `out` (same row0 convention).
+// Border clamps use the FULL image height H / width W (true borders only; band seams read real halo).
+struct CnnArgs {
+    const uint8_t* y;
+    size_t pitch;
+    int W, H;
+    int row0, rows;
+    int out_begin, out_end;
+    uint8_t* out;
+    size_t out_pitch;
+};
+int launch_cnn_fp32(Ctx* c, const CnnArgs& a, float* act2_out /* optional full act2 dump, may be null */);
+int launch_cnn_tc(Ctx* c, const CnnArgs& a);
+int tc_prepare_weights(Ctx* c, const float* params);
+void tc_release(Ctx* c);
+
+}  // namespace srcnn
+
+struct srcnn_ctx : public srcnn::Ctx {};
