@@ -167,7 +167,9 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    stream = torch.cuda.current_stream()
+    # an explicit non-default stream: the library launches on it and torch's events are recorded on it
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     eng = S.Engine(device=local_rank, variant=S.VARIANT_FP32 if args.variant == "fp32" else S.VARIANT_TC,
                    stream=stream.cuda_stream)
 

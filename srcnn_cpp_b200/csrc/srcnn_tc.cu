@@ -22,13 +22,20 @@
 //   * The reference's two border clamps are reproduced exactly: conv1 reads the replicate-clamped Y
 //     (applied when the tile is staged), conv3 reads act2 AT THE CLAMPED PIXEL (src/srcnn.cpp:203,209)
 //     -- implemented by folding the out-of-image taps onto the edge column/row of T, never by padding.
-//   * Two independent warpgroups per CTA (each owns 256 TMEM columns, its own Y ring and barriers)
-//     ping-pong on the tensor pipe: while one runs its CUDA-core epilogue the other's MMAs execute.
-//     The 150 KB of packed weights are fetched once per CTA with cp.async.bulk (TMA) and shared.
+//   * Biases ride on the tensor pipe too: one extra K=16 MMA whose A operand is a constant "ones" tile
+//     and whose B operand holds hi+lo FP16 halves of the FP32 bias (error < 1e-4), so the epilogues
+//     are pure ReLU+pack (cvt.rn.relu.f16x2.f32).
+//   * Two independent pipelines per CTA (one warpgroup each, one thread per TMEM lane; each owns 256
+//     TMEM columns, its own Y ring and barriers) ping-pong on the tensor pipe: while one runs its
+//     CUDA-core epilogue the other's MMAs execute.  A third warpgroup holds the two MMA-issuer
+//     threads, so a full tensor queue never stalls an epilogue.  Epilogue TMEM loads are software-
+//     pipelined (tcgen05.ld round trips are ~150 cycles).  The 163 KB of packed operands are fetched
+//     once per CTA with cp.async.bulk (TMA) and shared by both pipelines.
 //
-// Executed tensor work per pixel: conv1 2*16*9*64 = 18 432 FLOP (K efficiency 9/16), conv2 4 096,
-// conv3 2 048; algorithmic 16 064 FLOP/px is what bench.py reports against the roofline.
+// Executed tensor work per pixel: conv1 2*16*(9+1)*64 = 20 480 FLOP (K efficiency 9/16, +1 bias MMA),
+// conv2 5 120, conv3 2 048; algorithmic 16 064 FLOP/px is what bench.py reports against the roofline.
 #include <cuda_fp16.h>
+#include <cstdlib>
 
 #include "common.h"
 
@@ -47,18 +54,27 @@ constexpr int kB1Tile = 256 * 16 * 2;             // one Toeplitz B tile [256][1
 constexpr int kB1Bytes = 2 * 9 * kB1Tile;         // [half][kernel row]
 constexpr int kB2Bytes = 4 * 32 * 16 * 2;         // [k step][32][16]
 constexpr int kB3Bytes = 2 * 32 * 16 * 2;         // [k step][32 taps (25 used)][16]
-constexpr int kWeightBytes = kB1Bytes + kB2Bytes + kB3Bytes;  // 153 600
-constexpr int kHxBytes = 5 * 4 * 128 * 4;         // vertical-tap exchange: [m][col][lane] fp32
+constexpr int kBias1Bytes = kB1Tile;              // [256][16]: k=0 hi(b1), k=1 lo(b1)  (bias as one more MMA)
+constexpr int kBias2Bytes = 32 * 16 * 2;          // [32][16]:  k=0 hi(b2), k=1 lo(b2)
+constexpr int kOnesBytes = 2 * 128 * 16;          // A operand of the bias MMAs: chunk0 = [1,1,0..0] per row, chunk1 = 0
+constexpr int kWeightBytes = kB1Bytes + kB2Bytes + kB3Bytes + kBias1Bytes + kBias2Bytes + kOnesBytes;  // 166 912
+constexpr int kNV = 6;                            // vertical-tap partial planes: m0,m1,m2,(m3,n0),(m3,n1..4),m4
+constexpr int kHxBytes = kNV * 4 * 128 * 4;       // vertical-tap exchange: [plane][col][lane] fp32
 
 constexpr int kOffW = 0;
+constexpr int kImgB2 = kOffW + kB1Bytes;
+constexpr int kImgB3 = kImgB2 + kB2Bytes;
+constexpr int kOffBias1 = kImgB3 + kB3Bytes;
+constexpr int kOffBias2 = kOffBias1 + kBias1Bytes;
+constexpr int kOffOnes = kOffBias2 + kBias2Bytes;
 constexpr int kOffRing = kOffW + kWeightBytes;
 constexpr int kOffHx = kOffRing + 2 * kRingBytes;
 constexpr int kOffBar = kOffHx + 2 * kHxBytes;    // 1 weight barrier + 2 x 3 pipeline barriers
-constexpr int kOffTmem = kOffBar + 8 * 8;
+constexpr int kOffTmem = kOffBar + 24 * 8;
+constexpr int kThreads = 384;                    // 2 pipeline warpgroups + 1 warpgroup holding the 2 MMA issuers
 constexpr int kSmemBytes = kOffTmem + 64;
+static_assert(kWeightBytes % 64 == 0 && kSmemBytes <= 227 * 1024, "shared memory budget");
 
-__constant__ float c_b1[kC1];
-__constant__ float c_b2[kC2];
 __constant__ float c_b3;
 
 // ---------------------------------------------------------------------------------------------
@@ -72,6 +88,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
@@ -176,6 +195,16 @@ __device__ __forceinline__ uint32_t relu_pack_f16x2(float lo, float hi) {
     return r;
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : TM_R(v, 0), TM_R(v, 8)
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), TM_W(v, 0) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // kernel parameters
 // ---------------------------------------------------------------------------------------------
@@ -188,57 +217,132 @@ struct Params {
     uint8_t* out;          // same row0 convention as y
     size_t out_pitch;
     int out_aligned4;
+    int y_aligned2;
     const uint8_t* wimg;   // packed FP16 operand image (kWeightBytes)
     int gpb;               // column groups per band = ceil(W/4)
     long long total_groups;
     int* guard;
+    long long* dbg;        // optional timeline (SRCNN_TC_DEBUG=1): clock64 stamps of CTA 0
 };
+#define TL(slot) do { if (p.dbg && blockIdx.x == 0 && tp == 0 && g < 24) p.dbg[((pipe * 24 + g) * 8) + (slot)] = clock64(); } while (0)
+
+// One horizontal tap of conv3 (compile-time column D of the group, horizontal tap N, vertical tap M):
+// adds T to the output-window column it belongs to, plus the reference's clamped reads at the image's
+// left/right edge (act2[clamp(c+n-2)], src/srcnn.cpp:209): an edge column stands in for its
+// out-of-image neighbours.
+template <int D, int N, int M>
+__device__ __forceinline__ void tap_add(float (&acc)[8][5], float val, bool left, bool right) {
+    acc[D - N + 4][M] += val;
+    if (left) {
+        if (N == 0) { acc[D + 3][M] += val; acc[D + 2][M] += val; }
+        if (N == 1) { acc[D + 2][M] += val; }
+    }
+    if (right) {
+        if (N == 3) { acc[D + 2][M] += val; }
+        if (N == 4) { acc[D + 2][M] += val; acc[D + 1][M] += val; }
+    }
+}
+template <int D>
+__device__ __forceinline__ void taps_col(float (&acc)[8][5], const uint32_t* tv, bool l, bool r) {
+#define TAPROW(M_)                                                   \
+    tap_add<D, 0, M_>(acc, __uint_as_float(tv[M_ * 5 + 0]), l, r);   \
+    tap_add<D, 1, M_>(acc, __uint_as_float(tv[M_ * 5 + 1]), l, r);   \
+    tap_add<D, 2, M_>(acc, __uint_as_float(tv[M_ * 5 + 2]), l, r);   \
+    tap_add<D, 3, M_>(acc, __uint_as_float(tv[M_ * 5 + 3]), l, r);   \
+    tap_add<D, 4, M_>(acc, __uint_as_float(tv[M_ * 5 + 4]), l, r);
+    TAPROW(0) TAPROW(1) TAPROW(2) TAPROW(3) TAPROW(4)
+#undef TAPROW
+}
 
 // ---------------------------------------------------------------------------------------------
-// the kernel
+// the kernel: 12 warps.  Warpgroups 0 and 1 are two independent pipelines (one thread per TMEM lane:
+// 128 image rows each); warpgroup 2 holds the two MMA-issuer threads (warp 8 lane 0 -> pipeline 0,
+// warp 9 lane 0 -> pipeline 1).  A pipeline owns 256 TMEM columns, a Y ring, an exchange buffer and
+// six mbarriers; while it runs a CUDA-core epilogue the other pipeline's MMAs keep the tensor pipe busy.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 1) k_srcnn_tc(const Params p) {
+__global__ void __launch_bounds__(kThreads, 1) k_srcnn_tc(const Params p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x;
-    const int wg = tid >> 7;        // warpgroup: an independent pipeline
-    const int t = tid & 127;        // TMEM lane of this thread = image row R0 + t
     const int warp = tid >> 5;
+    const bool issuer = warp >= 8;
+    const int pipe = issuer ? (warp & 1) : (tid >> 7);   // independent pipeline
+    const int tp = tid & 127;        // thread within the pipeline = TMEM lane = image row R0 + tp
+    const int quarter = warp & 3;    // TMEM lane quarter this warp may access
     const uint32_t sbase = smem_u32(smem);
     const uint32_t wbar = sbase + kOffBar;
-    const uint32_t mb0 = sbase + kOffBar + 8 + wg * 24, mb1 = mb0 + 8, mb2 = mb0 + 16;
+    // per pipeline: mb0..2 = "conv1/2/3 MMAs complete" (tcgen05.commit), rq0..2 = "operands of conv1/2/3
+    // are ready" (128 epilogue-thread arrivals each)
+    const uint32_t mb0 = sbase + kOffBar + 8 + pipe * 48, mb1 = mb0 + 8, mb2 = mb0 + 16;
+    const uint32_t rq0 = mb0 + 24;
     volatile uint32_t* tmem_slot = (volatile uint32_t*)(smem + kOffTmem);
 
     if (tid == 0) {
         mbar_init(wbar, 1);
-        for (int i = 0; i < 6; i++) mbar_init(sbase + kOffBar + 8 + i * 8, 1);
+        for (int q = 0; q < 2; q++)
+            for (int i = 0; i < 6; i++) mbar_init(sbase + kOffBar + 8 + q * 48 + i * 8, i == 0 ? 2 : (i < 3 ? 4 : 128));
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(smem_u32((const void*)tmem_slot), 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (tid == 0) {  // weights: one TMA bulk fetch per CTA, shared by both warpgroups
+    if (tid == 0) {  // weights: one TMA bulk fetch per CTA, shared by both pipelines
         mbar_expect_tx(wbar, kWeightBytes);
         constexpr int kPiece = kWeightBytes / 4;
+        static_assert(kPiece % 16 == 0, "bulk copy granularity");
         for (int i = 0; i < 4; i++) bulk_g2s(sbase + kOffW + i * kPiece, p.wimg + i * kPiece, kPiece, wbar);
     }
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tm = tmem_base + wg * 256;                           // this warpgroup's 256 columns
-    const uint32_t tml = tm + ((uint32_t)((warp & 3) * 32) << 16);      // + this warp's lane quarter
-    const uint32_t ring = sbase + kOffRing + wg * kRingBytes;
-    uint8_t* ring_p = smem + kOffRing + wg * kRingBytes;
-    float* hx = (float*)(smem + kOffHx + wg * kHxBytes);
-    const int bar_id = 1 + wg;
-    uint32_t ph0 = 0, ph1 = 0, ph2 = 0;
+    const uint32_t tm = tmem_base + pipe * 256;                         // this pipeline's 256 columns
+    const uint32_t tml = tm + ((uint32_t)(quarter * 32) << 16);         // + this warp's lane quarter
+    const uint32_t ring = sbase + kOffRing + pipe * kRingBytes;
+    uint8_t* ring_p = smem + kOffRing + pipe * kRingBytes;
+    float* hx = (float*)(smem + kOffHx + pipe * kHxBytes);
+    const int pbar = 1 + pipe;                    // named barrier of the pipeline (128 threads)
 
     mbar_wait(wbar, 0, p.guard, 1);
 
     const int W = p.W, H = p.H;
     const long long nworkers = (long long)gridDim.x * 2;
-    const long long wk = (long long)blockIdx.x * 2 + wg;
+    const long long wk = (long long)blockIdx.x * 2 + pipe;
     long long lin = p.total_groups * wk / nworkers;
     const long long lin_end = p.total_groups * (wk + 1) / nworkers;
 
+    if (issuer) {
+        // ---------------- conv1 issuers: two threads per pipeline, each owns one N=128 half of D1 ----------------
+        // (a tcgen05.mma costs its issuing thread ~100-120 cycles whatever N is -- tools/microbench/mma_rate2.cu --
+        //  so the ten conv1 MMAs are split over two threads, and the short conv2/conv3 batches are issued by
+        //  the four epilogue warps themselves, one output column each)
+        if ((tid & 31) == 0) {
+            const int half_n = (warp >> 1) & 1;          // warps 8,9 -> D1 columns [0,128); warps 10,11 -> [128,256)
+            const uint32_t dcol = tm + half_n * 128;
+            const uint32_t bofs = half_n * 2048;         // rows 128..255 of a [256][16] no-swizzle tile
+            uint32_t q0 = 0;
+            while (lin < lin_end) {
+                const int band = (int)(lin / p.gpb);
+                const int gfirst = (int)(lin - (long long)band * p.gpb);
+                const int ng = (int)min((long long)(p.gpb - gfirst), lin_end - lin);
+                lin += ng;
+                const int s = gfirst * 4;
+                const int e = min(W, s + ng * 4);
+                const int G = (e - s + 3) / 4 + 1;
+                for (int g = 0; g < G; g++) {
+                    mbar_wait(rq0, q0, p.guard, 5);
+                    q0 ^= 1;
+                    tc_fence_after();
+                    const int j = g >> 1, half = g & 1;
+                    const uint32_t a0 = ring + (j & (kRingSlots - 1)) * kChunkBytes;
+                    const uint32_t b0 = sbase + kOffW + half * 9 * kB1Tile + bofs;
+                    mma_ss(dcol, smem_desc(sbase + kOffOnes, 2048, 128), smem_desc(sbase + kOffBias1 + bofs, 4096, 128), idesc_f16(128), 0);
+#pragma unroll
+                    for (int i = 0; i < 9; i++)
+                        mma_ss(dcol, smem_desc(a0 + i * 16, kChunkBytes, 128), smem_desc(b0 + i * kB1Tile, 4096, 128), idesc_f16(128), 1);
+                    mma_commit(mb0);
+                }
+            }
+        }
+    } else {
+    uint32_t ph0 = 0, ph1 = 0, ph2 = 0;
     while (lin < lin_end) {
         // ---- one segment: band `band`, output columns [s, e) ----
         const int band = (int)(lin / p.gpb);
@@ -253,172 +357,217 @@ __global__ void __launch_bounds__(256, 1) k_srcnn_tc(const Params p) {
         const int G = (e - s + 3) / 4 + 1;        // T groups: group g covers T columns s-2+4g .. s+1+4g
         const int jlast = (G - 1) >> 1;           // last step; needs Y chunks jlast, jlast+1
 
-        // stage one 8-pixel Y chunk (FP16, replicate-clamped) into the ring
-        auto load_chunk = [&](int q) {
-            const int slot = q & (kRingSlots - 1);
-            const int c0 = s - 6 + 8 * q;
-            for (int tr = t; tr < kTileRows; tr += 128) {
-                int r = min(max(R0 - 4 + tr, 0), H - 1);
-                r = min(max(r - p.row0, 0), p.rows - 1);
-                const uint8_t* src = p.y + (size_t)r * p.pitch;
-                uint32_t h[4];
+        // staged Y rows of this thread: tile row tp, and tile row 128+tp for the first 8 threads
+        const uint8_t* yrow0;
+        const uint8_t* yrow1;
+        {
+            int r = min(max(R0 - 4 + tp, 0), H - 1);
+            r = min(max(r - p.row0, 0), p.rows - 1);
+            yrow0 = p.y + (size_t)r * p.pitch;
+            r = min(max(R0 - 4 + 128 + (tp & 7), 0), H - 1);
+            r = min(max(r - p.row0, 0), p.rows - 1);
+            yrow1 = p.y + (size_t)r * p.pitch;
+        }
+        // 8 pixels of chunk q of one row -> two packed words (global loads; conversion happens at store time)
+        auto fetch_row = [&](const uint8_t* yrow, int c0, uint32_t& lo, uint32_t& hi) {
+            if (c0 >= 0 && c0 + 7 < W && p.y_aligned2) {
+                const unsigned short* q16 = reinterpret_cast<const unsigned short*>(yrow + c0);
+                lo = (uint32_t)q16[0] | ((uint32_t)q16[1] << 16);
+                hi = (uint32_t)q16[2] | ((uint32_t)q16[3] << 16);
+            } else {
+                lo = hi = 0;
 #pragma unroll
                 for (int x = 0; x < 4; x++) {
-                    const int ca = min(max(c0 + 2 * x, 0), W - 1), cb = min(max(c0 + 2 * x + 1, 0), W - 1);
-                    const __half2 v = __halves2half2(__int2half_rn((int)src[ca]), __int2half_rn((int)src[cb]));
-                    h[x] = *reinterpret_cast<const uint32_t*>(&v);
+                    lo |= (uint32_t)yrow[min(max(c0 + x, 0), W - 1)] << (8 * x);
+                    hi |= (uint32_t)yrow[min(max(c0 + 4 + x, 0), W - 1)] << (8 * x);
                 }
-                const uint4 v4 = make_uint4(h[0], h[1], h[2], h[3]);
-                *reinterpret_cast<uint4*>(ring_p + slot * kChunkBytes + tr * 16) = v4;
-                if (slot == 0) *reinterpret_cast<uint4*>(ring_p + kRingSlots * kChunkBytes + tr * 16) = v4;
             }
         };
-        // conv1 of group g: 9 Toeplitz MMAs, one per kernel row, accumulate into D1 = columns [0,256)
-        auto issue_conv1 = [&](int g) {
-            const int j = g >> 1, half = g & 1;
-            const uint32_t a0 = ring + (j & (kRingSlots - 1)) * kChunkBytes;
-            const uint32_t b0 = sbase + kOffW + half * 9 * kB1Tile;
+        // bytes -> FP16 via the 0x6400 (=1024.0) exponent trick, exact for 0..255; 16 B store into the ring
+        auto store_row = [&](int q, int tr, uint32_t lo, uint32_t hi) {
+            const int slot = q & (kRingSlots - 1);
+            const __half2 k1024 = __half2half2(__ushort_as_half((unsigned short)0x6400));
+            uint32_t h[4];
+            const uint32_t w[4] = {__byte_perm(lo, 0x64646464u, 0x4140), __byte_perm(lo, 0x64646464u, 0x4342),
+                                   __byte_perm(hi, 0x64646464u, 0x4140), __byte_perm(hi, 0x64646464u, 0x4342)};
 #pragma unroll
-            for (int i = 0; i < 9; i++)
-                mma_ss(tm, smem_desc(a0 + i * 16, kChunkBytes, 128), smem_desc(b0 + i * kB1Tile, 4096, 128), idesc_f16(256), i > 0);
-            mma_commit(mb0);
+            for (int x = 0; x < 4; x++) {
+                const __half2 v = __hsub2(*reinterpret_cast<const __half2*>(&w[x]), k1024);
+                h[x] = *reinterpret_cast<const uint32_t*>(&v);
+            }
+            const uint4 v4 = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(ring_p + slot * kChunkBytes + tr * 16) = v4;
+            if (slot == 0) *reinterpret_cast<uint4*>(ring_p + kRingSlots * kChunkBytes + tr * 16) = v4;
+        };
+        auto stage_chunk_now = [&](int q) {
+            const int c0 = s - 6 + 8 * q;
+            uint32_t lo, hi;
+            fetch_row(yrow0, c0, lo, hi);
+            store_row(q, tp, lo, hi);
+            if (tp < 8) {
+                fetch_row(yrow1, c0, lo, hi);
+                store_row(q, 128 + tp, lo, hi);
+            }
         };
 
-        load_chunk(0);
-        load_chunk(1);
+        stage_chunk_now(0);
+        stage_chunk_now(1);
         fence_proxy_async();
-        named_bar(bar_id, 128);
-        if (t == 0) {
-            tc_fence_after();
-            issue_conv1(0);
-        }
+        mbar_arrive(rq0);   // Y chunks 0,1 staged (and the previous segment is fully drained): conv1(0) may issue
 
-        float carry[4][5];
+        // horizontal-tap accumulators: window column cw <-> image column t0-2+cw; columns 0..3 finish in the
+        // current group, 4..7 are partial and slide down afterwards.  [.][m]: vertical tap
+        float acc[8][5];
 #pragma unroll
-        for (int a = 0; a < 4; a++)
+        for (int a = 0; a < 8; a++)
 #pragma unroll
-            for (int m = 0; m < 5; m++) carry[a][m] = 0.f;
+            for (int m = 0; m < 5; m++) acc[a][m] = 0.f;
 
         for (int g = 0; g < G; g++) {
             const int j = g >> 1;
-            if ((g & 1) == 0 && j + 2 <= jlast + 1) {  // prefetch the chunk the next step needs
-                load_chunk(j + 2);
-                fence_proxy_async();
+            const bool prefetch = ((g & 1) == 0) && (j + 2 <= jlast + 1);
+            uint32_t pre0 = 0, pre1 = 0, pre2 = 0, pre3 = 0;
+            TL(0);
+            if (prefetch) {   // global-load latency hides behind conv1 + E1
+                fetch_row(yrow0, s - 6 + 8 * (j + 2), pre0, pre1);
+                if (tp < 8) fetch_row(yrow1, s - 6 + 8 * (j + 2), pre2, pre3);
             }
-            // ---------------- E1: D1 -> +b1, ReLU, FP16 -> A1 (in place, columns [0,128)) ----------------
+            // ---------------- E1: D1 -> ReLU, FP16 -> A1 (in place, columns [0,128)) ----------------
+            // software-pipelined: the TMEM loads of column d+1 are in flight while column d is packed
             mbar_wait(mb0, ph0, p.guard, 2);
+            TL(1);
             ph0 ^= 1;
             tc_fence_after();
+            {
+                uint32_t va[64], vb[64], r[32];
+                tmem_ld32(tml, va);
+                tmem_ld32(tml + 32, va + 32);
+                tc_wait_ld();
+                tmem_ld32(tml + 64, vb);
+                tmem_ld32(tml + 96, vb + 32);
 #pragma unroll
-            for (int d = 0; d < 4; d++) {
-                uint32_t v[64], r[32];
-                tmem_ld32(tml + d * 64, v);
-                tmem_ld32(tml + d * 64 + 32, v + 32);
+                for (int c = 0; c < 32; c++) r[c] = relu_pack_f16x2(__uint_as_float(va[2 * c]), __uint_as_float(va[2 * c + 1]));
+                tmem_st32(tml, r);
+                tc_wait_ld();
+                tmem_ld32(tml + 128, va);
+                tmem_ld32(tml + 160, va + 32);
+#pragma unroll
+                for (int c = 0; c < 32; c++) r[c] = relu_pack_f16x2(__uint_as_float(vb[2 * c]), __uint_as_float(vb[2 * c + 1]));
+                tmem_st32(tml + 32, r);
+                tc_wait_ld();
+                tmem_ld32(tml + 192, vb);
+                tmem_ld32(tml + 224, vb + 32);
+#pragma unroll
+                for (int c = 0; c < 32; c++) r[c] = relu_pack_f16x2(__uint_as_float(va[2 * c]), __uint_as_float(va[2 * c + 1]));
+                tmem_st32(tml + 64, r);
                 tc_wait_ld();
 #pragma unroll
-                for (int c = 0; c < 32; c++)
-                    r[c] = relu_pack_f16x2(__uint_as_float(v[2 * c]) + c_b1[2 * c], __uint_as_float(v[2 * c + 1]) + c_b1[2 * c + 1]);
-                tmem_st32(tml + d * 32, r);
+                for (int c = 0; c < 32; c++) r[c] = relu_pack_f16x2(__uint_as_float(vb[2 * c]), __uint_as_float(vb[2 * c + 1]));
+                tmem_st32(tml + 96, r);
+            }
+            if (prefetch) {
+                store_row(j + 2, tp, pre0, pre1);
+                if (tp < 8) store_row(j + 2, 128 + tp, pre2, pre3);
+                fence_proxy_async();
             }
             tc_wait_st();
             tc_fence_before();
-            named_bar(bar_id, 128);
-            if (t == 0) {  // conv2: per column d, D2[d] = A1[d] (TMEM) x W2, K = 64 in 4 steps
+            TL(2);
+            named_bar(pbar, 128);   // A1 complete for all 128 lanes
+            if ((tid & 31) == 0) {  // conv2 of column d = this warp: D2[d] = b2 + A1[d] (TMEM) x W2, K = 64 in 4 steps
                 tc_fence_after();
-                const uint32_t b2 = sbase + kOffW + kB1Bytes;
+                const int d = quarter;
+                mma_ss(tm + 128 + d * 32, smem_desc(sbase + kOffOnes, 2048, 128), smem_desc(sbase + kOffBias2, 512, 128), idesc_f16(32), 0);
 #pragma unroll
-                for (int d = 0; d < 4; d++)
-#pragma unroll
-                    for (int ks = 0; ks < 4; ks++)
-                        mma_ts(tm + 128 + d * 32, tm + d * 32 + ks * 8, smem_desc(b2 + ks * 1024, 512, 128), idesc_f16(32), ks > 0);
+                for (int ks = 0; ks < 4; ks++)
+                    mma_ts(tm + 128 + d * 32, tm + d * 32 + ks * 8, smem_desc(sbase + kImgB2 + ks * 1024, 512, 128), idesc_f16(32), 1);
                 mma_commit(mb1);
             }
-            // ---------------- E2: D2 -> +b2, ReLU, FP16 -> A2 (in place, columns [128,192)) ----------------
+            __syncwarp();
+            // ---------------- E2: D2 -> ReLU, FP16 -> A2 (in place, columns [128,192)) ----------------
             mbar_wait(mb1, ph1, p.guard, 3);
+            TL(3);
             ph1 ^= 1;
             tc_fence_after();
+            {
+                uint32_t va[32], vb[32], r[16];
+                tmem_ld32(tml + 128, va);
+                tc_wait_ld();
+                tmem_ld32(tml + 160, vb);
 #pragma unroll
-            for (int d = 0; d < 4; d++) {
-                uint32_t v[32], r[16];
-                tmem_ld32(tml + 128 + d * 32, v);
+                for (int c = 0; c < 16; c++) r[c] = relu_pack_f16x2(__uint_as_float(va[2 * c]), __uint_as_float(va[2 * c + 1]));
+                tmem_st16(tml + 128, r);
+                tc_wait_ld();
+                tmem_ld32(tml + 192, va);
+#pragma unroll
+                for (int c = 0; c < 16; c++) r[c] = relu_pack_f16x2(__uint_as_float(vb[2 * c]), __uint_as_float(vb[2 * c + 1]));
+                tmem_st16(tml + 144, r);
+                tc_wait_ld();
+                tmem_ld32(tml + 224, vb);
+#pragma unroll
+                for (int c = 0; c < 16; c++) r[c] = relu_pack_f16x2(__uint_as_float(va[2 * c]), __uint_as_float(va[2 * c + 1]));
+                tmem_st16(tml + 160, r);
                 tc_wait_ld();
 #pragma unroll
-                for (int c = 0; c < 16; c++)
-                    r[c] = relu_pack_f16x2(__uint_as_float(v[2 * c]) + c_b2[2 * c], __uint_as_float(v[2 * c + 1]) + c_b2[2 * c + 1]);
-                tmem_st16(tml + 128 + d * 16, r);
+                for (int c = 0; c < 16; c++) r[c] = relu_pack_f16x2(__uint_as_float(vb[2 * c]), __uint_as_float(vb[2 * c + 1]));
+                tmem_st16(tml + 176, r);
             }
             tc_wait_st();
             tc_fence_before();
-            named_bar(bar_id, 128);
-            if (t == 0) {  // conv3 tap GEMM: T[d][tap] = A2[d] (TMEM) x W3, K = 32 in 2 steps -> columns [0,128)
+            TL(4);
+            named_bar(pbar, 128);   // A2 complete for all 128 lanes
+            if ((tid & 31) == 0) {  // conv3 tap GEMM of column d = this warp: T[d] = A2[d] (TMEM) x W3, K = 32 in 2 steps
                 tc_fence_after();
-                const uint32_t b3 = sbase + kOffW + kB1Bytes + kB2Bytes;
+                const int d = quarter;
 #pragma unroll
-                for (int d = 0; d < 4; d++)
-#pragma unroll
-                    for (int ks = 0; ks < 2; ks++)
-                        mma_ts(tm + d * 32, tm + 128 + d * 16 + ks * 8, smem_desc(b3 + ks * 1024, 512, 128), idesc_f16(32), ks > 0);
+                for (int ks = 0; ks < 2; ks++)
+                    mma_ts(tm + d * 32, tm + 128 + d * 16 + ks * 8, smem_desc(sbase + kImgB3 + ks * 1024, 512, 128), idesc_f16(32), ks > 0);
                 mma_commit(mb2);
             }
+            __syncwarp();
             // ---------------- E3a: horizontal taps in registers ----------------
             mbar_wait(mb2, ph2, p.guard, 4);
+            TL(5);
             ph2 ^= 1;
             tc_fence_after();
             const int t0 = s - 2 + 4 * g;  // first T column of this group
-            float acc[8][5];               // window column cw <-> image column t0-2+cw; [vertical tap m]
-#pragma unroll
-            for (int a = 0; a < 4; a++)
-#pragma unroll
-                for (int m = 0; m < 5; m++) {
-                    acc[a][m] = carry[a][m];
-                    acc[a + 4][m] = 0.f;
-                }
-#pragma unroll
-            for (int d = 0; d < 4; d++) {
-                uint32_t tv[32];
-                tmem_ld32(tml + d * 32, tv);
+            {
+                uint32_t ta[32], tb[32];
+                tmem_ld32(tml, ta);
                 tc_wait_ld();
-                const int cp = t0 + d;  // image column of this T column (warp-uniform)
-                if (cp >= 0 && cp < W) {
-#pragma unroll
-                    for (int m = 0; m < 5; m++)
-#pragma unroll
-                        for (int n = 0; n < 5; n++) acc[d - n + 4][m] += __uint_as_float(tv[m * 5 + n]);
-                    if (cp == 0) {  // columns -1 and -2 read act2 at column 0 (src/srcnn.cpp:209)
-#pragma unroll
-                        for (int m = 0; m < 5; m++) {
-                            acc[d + 3][m] += __uint_as_float(tv[m * 5]);
-                            acc[d + 2][m] += __uint_as_float(tv[m * 5]) + __uint_as_float(tv[m * 5 + 1]);
-                        }
-                    }
-                    if (cp == W - 1) {  // columns W and W+1 read act2 at column W-1
-#pragma unroll
-                        for (int m = 0; m < 5; m++) {
-                            acc[d + 2][m] += __uint_as_float(tv[m * 5 + 3]) + __uint_as_float(tv[m * 5 + 4]);
-                            acc[d + 1][m] += __uint_as_float(tv[m * 5 + 4]);
-                        }
-                    }
-                }
+                tmem_ld32(tml + 32, tb);
+                if (t0 >= 0 && t0 < W) taps_col<0>(acc, ta, t0 == 0, t0 == W - 1);
+                tc_wait_ld();
+                tmem_ld32(tml + 64, ta);
+                if (t0 + 1 >= 0 && t0 + 1 < W) taps_col<1>(acc, tb, t0 + 1 == 0, t0 + 1 == W - 1);
+                tc_wait_ld();
+                tmem_ld32(tml + 96, tb);
+                if (t0 + 2 >= 0 && t0 + 2 < W) taps_col<2>(acc, ta, t0 + 2 == 0, t0 + 2 == W - 1);
+                tc_wait_ld();
+                if (t0 + 3 >= 0 && t0 + 3 < W) taps_col<3>(acc, tb, t0 + 3 == 0, t0 + 3 == W - 1);
             }
             // vertical taps cross lanes: publish the 4 finished columns
 #pragma unroll
             for (int m = 0; m < 5; m++)
 #pragma unroll
-                for (int a = 0; a < 4; a++) hx[(m * 4 + a) * 128 + t] = acc[a][m];
+                for (int a = 0; a < 4; a++) hx[(m * 4 + a) * 128 + tp] = acc[a][m];
+#pragma unroll
+            for (int a = 0; a < 4; a++)   // slide the window: the 4 partial columns become the next group's first 4
+#pragma unroll
+                for (int m = 0; m < 5; m++) { acc[a][m] = acc[a + 4][m]; acc[a + 4][m] = 0.f; }
             tc_fence_before();
-            named_bar(bar_id, 128);  // T fully read (D1 region reusable) and hx visible
-            if (t == 0 && g + 1 < G) {
-                tc_fence_after();
-                issue_conv1(g + 1);  // the tensor pipe starts the next group while we finish this one
-            }
-            // ---------------- E3b: vertical taps, bias, truncate, clamp, store ----------------
+            TL(6);
+            if (g + 1 < G) mbar_arrive(rq0);   // T fully read (D1 region reusable), next Y chunk staged
+            named_bar(pbar, 128);              // hx visible to the whole pipeline
+            TL(7);
+            // ---------------- E3b: vertical taps, bias, truncate, clamp, store (4 columns per thread) ----------------
             {
-                const int row = R0 + t;
+                const int row = R0 + tp;
                 int ln[5];
 #pragma unroll
                 for (int m = 0; m < 5; m++) ln[m] = min(max(min(max(row + m - 2, 0), H - 1) - R0, 0), 127);  // src/srcnn.cpp:203
                 const int c0 = t0 - 2;
-                const bool row_ok = (t >= 2) && (t <= 125) && (row >= band_begin) && (row < band_end);
+                const bool row_ok = (tp >= 2) && (tp <= 125) && (row >= band_begin) && (row < band_end);
                 uint32_t pk = 0;
                 int px[4];
 #pragma unroll
@@ -443,13 +592,10 @@ __global__ void __launch_bounds__(256, 1) k_srcnn_tc(const Params p) {
                     }
                 }
             }
-#pragma unroll
-            for (int a = 0; a < 4; a++)
-#pragma unroll
-                for (int m = 0; m < 5; m++) carry[a][m] = acc[a + 4][m];
         }
-        // segment done: every MMA of this warpgroup has been waited for; hx reads of the last group
-        // must finish before the next segment's first hx write -> covered by its first named barriers
+        // segment done: every MMA of this pipeline has been waited for; the hx reads of the last group
+        // finish before the next segment's first hx write (conv3 of the next group needs all 128 arrivals)
+    }
     }
 
     tc_fence_before();
@@ -568,11 +714,32 @@ int tc_prepare_weights(Ctx* c, const float* P) {
             for (int k = 0; k < 16; k++)
                 put_h(img.data(), kB1Bytes + kB2Bytes + (size_t)ks * 1024 + (size_t)(k / 8) * 512 + (size_t)n * 16 + (k % 8) * 2,
                       n < 25 ? w3[(ks * 16 + k) * 25 + n] : 0.f);
+    // bias tiles: FP32 bias = hi + lo in FP16, multiplied by the two 1.0 columns of the "ones" A tile
+    auto hi_lo = [](float b, float& hi, float& lo) {
+        hi = __half2float(__float2half_rn(b));
+        lo = b - hi;
+    };
+    for (int d = 0; d < 4; d++)
+        for (int ch = 0; ch < 64; ch++) {
+            float hi, lo;
+            hi_lo(P[kOffB1 + ch], hi, lo);
+            const size_t n = (size_t)d * 64 + ch;
+            put_h(img.data(), kOffBias1 + n * 16 + 0, hi);
+            put_h(img.data(), kOffBias1 + n * 16 + 2, lo);
+        }
+    for (int n = 0; n < 32; n++) {
+        float hi, lo;
+        hi_lo(P[kOffB2 + n], hi, lo);
+        put_h(img.data(), kOffBias2 + (size_t)n * 16 + 0, hi);
+        put_h(img.data(), kOffBias2 + (size_t)n * 16 + 2, lo);
+    }
+    for (int r = 0; r < 128; r++) {  // ones tile: K chunk 0 = [1,1,0,0,0,0,0,0] per row, K chunk 1 = 0
+        put_h(img.data(), kOffOnes + (size_t)r * 16 + 0, 1.0f);
+        put_h(img.data(), kOffOnes + (size_t)r * 16 + 2, 1.0f);
+    }
     SRCNN_CUDA(c, cudaMalloc(&c->d_tc_weights, kWeightBytes));
     c->tc_weights_bytes = kWeightBytes;
     SRCNN_CUDA(c, cudaMemcpy(c->d_tc_weights, img.data(), kWeightBytes, cudaMemcpyHostToDevice));
-    SRCNN_CUDA(c, cudaMemcpyToSymbol(tc::c_b1, P + kOffB1, sizeof(float) * kC1));
-    SRCNN_CUDA(c, cudaMemcpyToSymbol(tc::c_b2, P + kOffB2, sizeof(float) * kC2));
     SRCNN_CUDA(c, cudaMemcpyToSymbol(tc::c_b3, P + kOffB3, sizeof(float)));
     SRCNN_CUDA(c, cudaFuncSetAttribute(tc::k_srcnn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     return SRCNN_OK;
@@ -593,21 +760,39 @@ int launch_cnn_tc(Ctx* c, const CnnArgs& a) {
     p.out_begin = a.out_begin; p.out_end = a.out_end;
     p.out = a.out; p.out_pitch = a.out_pitch;
     p.out_aligned4 = ((((uintptr_t)a.out) | a.out_pitch) & 3) == 0;
+    p.y_aligned2 = ((((uintptr_t)a.y) | a.pitch) & 1) == 0;
     p.wimg = (const uint8_t*)c->d_tc_weights;
     p.gpb = (a.W + 3) / 4;
     const int nbands = (a.out_end - a.out_begin + kBandRows - 1) / kBandRows;
     p.total_groups = (long long)nbands * p.gpb;
     p.guard = c->d_guard;
+    p.dbg = nullptr;
+    if (getenv("SRCNN_TC_DEBUG")) {
+        if (!c->work_buf.p) {
+            int rc = ensure(c, c->work_buf, 2 * 24 * 8 * sizeof(long long));
+            if (rc) return rc;
+        }
+        cudaMemsetAsync(c->work_buf.p, 0, 2 * 24 * 8 * sizeof(long long), c->stream);
+        p.dbg = (long long*)c->work_buf.p;
+    }
     // one persistent CTA per SM; fewer when the image is too small to give every warpgroup ~8 groups
     long long want = (p.total_groups + 15) / 16;
     int grid = (int)std::min<long long>(c->sm_count, std::max<long long>(1, want));
-    k_srcnn_tc<<<grid, 256, kSmemBytes, c->stream>>>(p);
+    k_srcnn_tc<<<grid, kThreads, kSmemBytes, c->stream>>>(p);
     c->launches++;
     SRCNN_CUDA(c, cudaGetLastError());
     return SRCNN_OK;
 }
 
 }  // namespace srcnn
+
+// debug hook: copies the last launch's timeline (2 pipelines x 24 groups x 8 stamps) to the host
+extern "C" __attribute__((visibility("default"))) int srcnn_debug_tc_timeline(srcnn_ctx* c, long long* out) {
+    if (!c || !c->work_buf.p) return SRCNN_E_ARG;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    return cudaMemcpy(out, c->work_buf.p, 2 * 24 * 8 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? SRCNN_OK : SRCNN_E_CUDA;
+}
 
 // test hook (not part of the stable ABI; exported for tests/test_tc_primitives.py)
 extern "C" __attribute__((visibility("default"))) int srcnn_debug_tc_selftest(srcnn_ctx* c, const void* d_a_tile,
