@@ -11,9 +11,9 @@ OBJ := build/obj
 LIB := srcnn_cpp_b200/libsrcnn_b200.so
 WEIGHTS := $(abspath srcnn_cpp_b200/data/srcnn_weights.bin)
 CU := api color_bicubic srcnn_fp32 srcnn_tc
-OBJS := $(addprefix $(OBJ)/,$(addsuffix .o,$(CU))) $(OBJ)/weights_blob.o
+OBJS := $(addprefix $(OBJ)/,$(addsuffix .o,$(CU))) $(OBJ)/weights_blob.o $(OBJ)/libsrcnn.o
 
-all: $(LIB) oracle
+all: $(LIB) bin/srcnn oracle
 
 $(OBJ)/%.o: $(CSRC)/%.cu $(CSRC)/common.h $(CSRC)/weights.h include/srcnn_b200.h
 	@mkdir -p $(OBJ)
@@ -23,6 +23,15 @@ $(OBJ)/%.o: $(CSRC)/%.cu $(CSRC)/common.h $(CSRC)/weights.h include/srcnn_b200.h
 $(OBJ)/weights_blob.o: $(CSRC)/weights_blob.c $(WEIGHTS)
 	@mkdir -p $(OBJ)
 	$(HOSTCC) -c -fPIC -DSRCNN_WEIGHTS_BIN='"$(WEIGHTS)"' $< -o $@
+
+$(OBJ)/libsrcnn.o: srcnn_cpp_b200/cli/libsrcnn.cpp include/libsrcnn.h include/srcnn_b200.h
+	@mkdir -p $(OBJ)
+	$(HOSTCXX) -std=c++17 -O2 -fPIC -fvisibility=hidden -c $< -o $@
+
+bin/srcnn: srcnn_cpp_b200/cli/srcnn_main.cpp srcnn_cpp_b200/cli/image_io.cpp srcnn_cpp_b200/cli/image_io.h $(LIB)
+	@mkdir -p bin
+	$(HOSTCXX) -std=c++17 -O2 srcnn_cpp_b200/cli/srcnn_main.cpp srcnn_cpp_b200/cli/image_io.cpp -o $@ \
+	    -Lsrcnn_cpp_b200 -lsrcnn_b200 -lz -lpthread -Wl,-rpath,'$$ORIGIN/../srcnn_cpp_b200'
 
 $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -shared -ccbin $(HOSTCXX) -Xcompiler -fPIC -o $@ $(OBJS) -lcuda

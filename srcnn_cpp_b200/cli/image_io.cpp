@@ -1,0 +1,203 @@
+// image_io.cpp -- PNG (zlib) and PPM/PGM codecs for the CLI.  See image_io.h.
+#include "image_io.h"
+
+#include <zlib.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+namespace {
+
+bool read_file(const std::string& path, std::vector<uint8_t>* buf) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    fseek(f, 0, SEEK_END);
+    long n = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    if (n < 0) { fclose(f); return false; }
+    buf->resize((size_t)n);
+    size_t got = n ? fread(buf->data(), 1, (size_t)n, f) : 0;
+    fclose(f);
+    return got == (size_t)n;
+}
+
+uint32_t be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+
+int paeth(int a, int b, int c) {
+    int p = a + b - c, pa = abs(p - a), pb = abs(p - b), pc = abs(p - c);
+    return (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
+}
+
+bool png_decode(const std::vector<uint8_t>& file, ImageBGR* out, std::string* err) {
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    if (file.size() < 8 || memcmp(file.data(), sig, 8) != 0) { *err = "not a PNG"; return false; }
+    size_t pos = 8;
+    uint32_t w = 0, h = 0;
+    int depth = 0, ctype = 0, interlace = 0;
+    std::vector<uint8_t> idat, plte, trns;
+    while (pos + 12 <= file.size()) {
+        uint32_t len = be32(&file[pos]);
+        const uint8_t* type = &file[pos + 4];
+        if (pos + 12 + (size_t)len > file.size()) { *err = "truncated PNG"; return false; }
+        const uint8_t* data = &file[pos + 8];
+        if (!memcmp(type, "IHDR", 4) && len >= 13) {
+            w = be32(data); h = be32(data + 4); depth = data[8]; ctype = data[9]; interlace = data[12];
+        } else if (!memcmp(type, "PLTE", 4)) {
+            plte.assign(data, data + len);
+        } else if (!memcmp(type, "tRNS", 4)) {
+            trns.assign(data, data + len);
+        } else if (!memcmp(type, "IDAT", 4)) {
+            idat.insert(idat.end(), data, data + len);
+        } else if (!memcmp(type, "IEND", 4)) {
+            break;
+        }
+        pos += 12 + (size_t)len;
+    }
+    if (w == 0 || h == 0) { *err = "PNG without IHDR"; return false; }
+    if (interlace) { *err = "interlaced PNG not supported"; return false; }
+    if (depth != 8 && depth != 16) { *err = "PNG bit depth not supported (8 or 16 only)"; return false; }
+    int ch = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
+    if (!ch || (ctype == 3 && depth != 8)) { *err = "PNG colour type not supported"; return false; }
+    const size_t bpp = (size_t)ch * depth / 8, stride = bpp * w;
+    std::vector<uint8_t> raw((stride + 1) * h);
+    uLongf rawlen = raw.size();
+    if (uncompress(raw.data(), &rawlen, idat.data(), idat.size()) != Z_OK || rawlen != raw.size()) { *err = "PNG inflate failed"; return false; }
+    std::vector<uint8_t> img(stride * h);
+    for (uint32_t y = 0; y < h; y++) {
+        const uint8_t ft = raw[y * (stride + 1)];
+        const uint8_t* src = &raw[y * (stride + 1) + 1];
+        uint8_t* cur = &img[y * stride];
+        const uint8_t* up = y ? &img[(y - 1) * stride] : nullptr;
+        for (size_t x = 0; x < stride; x++) {
+            int a = x >= bpp ? cur[x - bpp] : 0, b = up ? up[x] : 0, c = (up && x >= bpp) ? up[x - bpp] : 0, v = src[x];
+            switch (ft) {
+                case 0: break;
+                case 1: v += a; break;
+                case 2: v += b; break;
+                case 3: v += (a + b) >> 1; break;
+                case 4: v += paeth(a, b, c); break;
+                default: *err = "bad PNG filter"; return false;
+            }
+            cur[x] = (uint8_t)v;
+        }
+    }
+    out->w = (int)w; out->h = (int)h;
+    out->px.resize((size_t)w * h * 3);
+    const size_t step = depth / 8;  // 16-bit samples: keep the high byte (like cv::imread's 8-bit conversion)
+    for (size_t i = 0; i < (size_t)w * h; i++) {
+        const uint8_t* p = &img[i * bpp];
+        uint8_t r, g, b;
+        if (ctype == 0 || ctype == 4) { r = g = b = p[0]; }
+        else if (ctype == 3) {
+            const size_t k = (size_t)p[0] * 3;
+            if (k + 2 < plte.size()) { r = plte[k]; g = plte[k + 1]; b = plte[k + 2]; } else { r = g = b = 0; }
+        } else { r = p[0]; g = p[step]; b = p[2 * step]; }
+        out->px[3 * i] = b; out->px[3 * i + 1] = g; out->px[3 * i + 2] = r;  // alpha is dropped, like IMREAD_COLOR
+    }
+    return true;
+}
+
+void put_be32(std::vector<uint8_t>& v, uint32_t x) { v.push_back(x >> 24); v.push_back(x >> 16); v.push_back(x >> 8); v.push_back(x); }
+
+void png_chunk(std::vector<uint8_t>& out, const char* type, const uint8_t* data, size_t len) {
+    put_be32(out, (uint32_t)len);
+    size_t start = out.size();
+    out.insert(out.end(), type, type + 4);
+    if (len) out.insert(out.end(), data, data + len);
+    uint32_t crc = crc32(0, &out[start], (uInt)(len + 4));
+    put_be32(out, crc);
+}
+
+bool png_encode(const ImageBGR& img, std::vector<uint8_t>* file) {
+    const size_t stride = (size_t)img.w * 3;
+    std::vector<uint8_t> raw((stride + 1) * img.h);
+    for (int y = 0; y < img.h; y++) {
+        uint8_t* row = &raw[(size_t)y * (stride + 1)];
+        row[0] = 0;  // filter: none (deterministic and simple; zlib does the rest)
+        const uint8_t* s = &img.px[(size_t)y * stride];
+        for (int x = 0; x < img.w; x++) { row[1 + 3 * x] = s[3 * x + 2]; row[2 + 3 * x] = s[3 * x + 1]; row[3 + 3 * x] = s[3 * x]; }
+    }
+    uLongf clen = compressBound(raw.size());
+    std::vector<uint8_t> comp(clen);
+    if (compress2(comp.data(), &clen, raw.data(), raw.size(), 6) != Z_OK) return false;
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    file->assign(sig, sig + 8);
+    uint8_t ihdr[13];
+    ihdr[0] = img.w >> 24; ihdr[1] = img.w >> 16; ihdr[2] = img.w >> 8; ihdr[3] = img.w;
+    ihdr[4] = img.h >> 24; ihdr[5] = img.h >> 16; ihdr[6] = img.h >> 8; ihdr[7] = img.h;
+    ihdr[8] = 8; ihdr[9] = 2; ihdr[10] = 0; ihdr[11] = 0; ihdr[12] = 0;
+    png_chunk(*file, "IHDR", ihdr, 13);
+    png_chunk(*file, "IDAT", comp.data(), clen);
+    png_chunk(*file, "IEND", nullptr, 0);
+    return true;
+}
+
+bool pnm_decode(const std::vector<uint8_t>& f, ImageBGR* out, std::string* err) {
+    if (f.size() < 2 || f[0] != 'P' || (f[1] != '5' && f[1] != '6')) { *err = "not a binary PPM/PGM"; return false; }
+    const int ch = f[1] == '6' ? 3 : 1;
+    size_t pos = 2;
+    long vals[3];
+    for (int k = 0; k < 3; k++) {
+        for (;;) {
+            while (pos < f.size() && isspace(f[pos])) pos++;
+            if (pos < f.size() && f[pos] == '#') { while (pos < f.size() && f[pos] != '\n') pos++; continue; }
+            break;
+        }
+        long v = 0; bool any = false;
+        while (pos < f.size() && isdigit(f[pos])) { v = v * 10 + (f[pos] - '0'); pos++; any = true; }
+        if (!any) { *err = "bad PNM header"; return false; }
+        vals[k] = v;
+    }
+    pos++;  // single whitespace after maxval
+    if (vals[2] != 255 || vals[0] <= 0 || vals[1] <= 0) { *err = "only 8-bit PNM supported"; return false; }
+    const size_t n = (size_t)vals[0] * vals[1];
+    if (pos + n * ch > f.size()) { *err = "truncated PNM"; return false; }
+    out->w = (int)vals[0]; out->h = (int)vals[1]; out->px.resize(n * 3);
+    for (size_t i = 0; i < n; i++) {
+        const uint8_t* p = &f[pos + i * ch];
+        if (ch == 3) { out->px[3 * i] = p[2]; out->px[3 * i + 1] = p[1]; out->px[3 * i + 2] = p[0]; }
+        else { out->px[3 * i] = out->px[3 * i + 1] = out->px[3 * i + 2] = p[0]; }
+    }
+    return true;
+}
+
+std::string lower_ext(const std::string& path) {
+    size_t dot = path.find_last_of('.');
+    std::string e = dot == std::string::npos ? "" : path.substr(dot);
+    for (auto& c : e) c = (char)tolower(c);
+    return e;
+}
+
+}  // namespace
+
+bool image_read(const std::string& path, ImageBGR* out, std::string* err) {
+    std::vector<uint8_t> f;
+    if (!read_file(path, &f)) { *err = "cannot read file"; return false; }
+    if (f.size() >= 8 && f[0] == 0x89 && f[1] == 'P') return png_decode(f, out, err);
+    if (f.size() >= 2 && f[0] == 'P' && (f[1] == '5' || f[1] == '6')) return pnm_decode(f, out, err);
+    *err = "unsupported image format (PNG and binary PPM/PGM are supported)";
+    return false;
+}
+
+bool image_write(const std::string& path, const ImageBGR& img, std::string* err) {
+    std::vector<uint8_t> file;
+    const std::string e = lower_ext(path);
+    if (e == ".ppm" || e == ".pnm") {
+        char hdr[64];
+        int n = snprintf(hdr, sizeof(hdr), "P6\n%d %d\n255\n", img.w, img.h);
+        file.assign(hdr, hdr + n);
+        for (size_t i = 0; i < (size_t)img.w * img.h; i++) { file.push_back(img.px[3 * i + 2]); file.push_back(img.px[3 * i + 1]); file.push_back(img.px[3 * i]); }
+    } else if (e == ".png" || e.empty()) {
+        if (!png_encode(img, &file)) { *err = "PNG encode failed"; return false; }
+    } else {
+        *err = "unsupported output format '" + e + "' (use .png or .ppm)";
+        return false;
+    }
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) { *err = "cannot open output file"; return false; }
+    size_t put = fwrite(file.data(), 1, file.size(), f);
+    fclose(f);
+    if (put != file.size()) { *err = "short write"; return false; }
+    return true;
+}

@@ -1,0 +1,75 @@
+"""bin/srcnn drop-in: argument handling and exit codes on CPU; the cfg1 golden run on the GPU."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "bin", "srcnn")
+
+
+def _run(*args):
+    return subprocess.run([BIN, *args], capture_output=True, text=True, timeout=300)
+
+
+def test_help_and_no_args_return_zero():
+    for args in ((), ("--help",), ("--help", "x.png")):
+        r = _run(*args)
+        assert r.returncode == 0                                   # src/srcnn.cpp:709-715
+        assert "usage :" in r.stdout and "--scale=" in r.stdout and "--noverbose" in r.stdout
+
+
+def test_missing_source_is_exit_minus_one(tmp_path):
+    r = _run(str(tmp_path / "nope.png"))
+    assert r.returncode == 255                                     # t_exit_code = -1, src/srcnn.cpp:479
+    assert "- load failure :" in r.stdout
+    r = _run("--noverbose", str(tmp_path / "nope.png"))
+    assert r.returncode == 255 and r.stdout == ""
+
+
+@pytest.mark.gpu
+def test_cfg1_butterfly_via_cli_is_bit_exact(tmp_path):
+    """BASELINE configs[0]: Pictures/butterfly.png x1.5 via bin/srcnn == Pictures/butterfly-srcnn.png."""
+    import cv2
+    src = os.path.join(ROOT, "tests", "golden", "butterfly.png")
+    gold = cv2.imread(os.path.join(ROOT, "tests", "golden", "butterfly-srcnn.png"))
+    dst = str(tmp_path / "out.png")
+    r = _run("--scale=1.5", "--variant=fp32", src, dst)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "- Performace :" in r.stdout and "ms took." in r.stdout
+    assert np.array_equal(cv2.imread(dst), gold)
+    # tensor-core variant + default output name <stem>_resized<ext> (src/srcnn.cpp:396-416)
+    src2 = str(tmp_path / "b.png")
+    cv2.imwrite(src2, cv2.imread(src))
+    r = _run("--scale=1.5", "--noverbose", src2)
+    assert r.returncode == 0 and r.stdout == ""
+    out = cv2.imread(str(tmp_path / "b_resized.png"))
+    d = np.abs(out.astype(np.int16) - gold.astype(np.int16))
+    assert d.max() <= 3 and (d <= 1).mean() >= 0.999
+
+
+@pytest.mark.gpu
+def test_process_srcnn_library_entry(oracle):
+    """ProcessSRCNN(rgb, w, h, d, mul, out&, outsz&) -- src/test.cpp:347-361: ret == 0 and
+    outsz == (unsigned)(w*mul) * (unsigned)(h*mul) * d; RGB order in and out."""
+    import srcnn_cpp_b200 as S
+    L = S.load_library()
+    fn = L._Z12ProcessSRCNNPKhjjjfRPhRj
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, C.c_uint, C.c_uint, C.c_uint, C.c_float, C.POINTER(C.c_void_p), C.POINTER(C.c_uint)]
+    rng = np.random.default_rng(4)
+    bgr = rng.integers(0, 256, (20, 26, 3), dtype=np.uint8)
+    rgb = np.ascontiguousarray(bgr[:, :, ::-1])
+    out, sz = C.c_void_p(), C.c_uint()
+    assert fn(rgb.ctypes.data, 26, 20, 3, C.c_float(2.0), C.byref(out), C.byref(sz)) == 0
+    assert sz.value == 52 * 40 * 3
+    got = np.ctypeslib.as_array((C.c_uint8 * sz.value).from_address(out.value)).reshape(40, 52, 3)
+    want = oracle.pipeline(bgr, 2.0)[:, :, ::-1]
+    d = np.abs(got.astype(np.int16) - want.astype(np.int16))
+    assert d.max() <= 3 and (d <= 1).mean() >= 0.995
+    # 4-channel input keeps 4 channels (src/test.cpp: outsz uses d)
+    rgba = np.dstack([rgb, np.full((20, 26), 200, np.uint8)])
+    assert fn(np.ascontiguousarray(rgba).ctypes.data, 26, 20, 4, C.c_float(2.0), C.byref(out), C.byref(sz)) == 0
+    assert sz.value == 52 * 40 * 4
