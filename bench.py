@@ -268,7 +268,10 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "kernel": "k_srcnn_tc (fused conv1+conv2+conv3)" if args.variant != "fp32" else "k_conv99x11_strict+k_conv55_strict",
                          "achieved": achieved, "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16"],
-                         "traffic": None, "peak_source": peaks["src"], "kernel_ms": k_ms,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture of this
+                         # command (profiles/r1_summary.md); the Y' plane it writes stays in L2 for the merge kernel
+                         "traffic": (8.51e6 if args.variant != "fp32" else None),
+                         "peak_source": peaks["src"], "kernel_ms": k_ms,
                          "algorithmic_flop_per_launch": FLOP_PER_PX * px_step},
             "stages": {"colour_bicubic_ms": a_ms / max(1, calls), "srcnn_ms": k_ms, "merge_ms": c_ms / max(1, calls),
                        "colour_bicubic_GBs": a_gbs, "colour_bicubic_frac_hbm": a_gbs / peaks["hbm"],
