@@ -180,9 +180,18 @@ __global__ void __launch_bounds__(256) k_color_bicubic_direct(ResizeDev p) {
 constexpr int kTW = 64, kTH = 32;       // output tile
 constexpr int kMaxSC = 72, kMaxSR = 40; // footprint capacity (source cols / rows incl. the 3-tap apron)
 
+// round-half-even + saturate to 0..255 in one instruction (what v_round + v_pack_u do in cv::resize)
+__device__ __forceinline__ uint32_t sat_u8_rn(float v) {
+    uint32_t r;
+    asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return r;
+}
+
 __global__ void __launch_bounds__(256) k_color_bicubic_tiled(ResizeDev p) {
     __shared__ uint8_t sP[3][kMaxSR][kMaxSC];
-    __shared__ int sH[3][kMaxSR][kTW];
+    // horizontal sums kept as float: they are integers below 2^24, so the conversion is exact and is done
+    // once per sum instead of once per use in the vertical pass
+    __shared__ __align__(16) float sH[3][kMaxSR][kTW];
 
     const int dx0 = blockIdx.x * kTW;
     const int dy0 = p.row_begin + blockIdx.y * kTH;
@@ -192,7 +201,7 @@ __global__ void __launch_bounds__(256) k_color_bicubic_tiled(ResizeDev p) {
     const int nsc = sx_hi - sx_lo + 1, nsr = sy_hi - sy_lo + 1;
     const int tid = threadIdx.x;
 
-    // (1) colour-convert the footprint
+    // (1) colour-convert the footprint (replicate border applied here)
     for (int i = tid; i < nsr * nsc; i += 256) {
         const int r = i / nsc, c = i - r * nsc;
         const int gy = clampi(sy_lo + r, 0, p.sh - 1) - p.src_row0;
@@ -208,50 +217,59 @@ __global__ void __launch_bounds__(256) k_color_bicubic_tiled(ResizeDev p) {
     }
     __syncthreads();
 
-    // (2) horizontal pass: thread owns one output column (and a quarter of the footprint rows)
+    // (2) integer horizontal pass: thread owns one output column, walks footprint rows
     {
         const int col = tid & (kTW - 1);
         const int dx = dx0 + col;
         if (dx < dx1) {
             const int s = p.xofs[dx] - 1 - sx_lo;
             const short4 cx = p.xcoef[dx];
+            const int k0 = cx.x, k1 = cx.y, k2 = cx.z, k3 = cx.w;
             for (int r = tid >> 6; r < nsr; r += 256 / kTW) {
 #pragma unroll
                 for (int pl = 0; pl < 3; pl++) {
                     const uint8_t* q = &sP[pl][r][s];
-                    sH[pl][r][col] = (int)q[0] * cx.x + (int)q[1] * cx.y + (int)q[2] * cx.z + (int)q[3] * cx.w;
+                    sH[pl][r][col] = (float)((int)q[0] * k0 + (int)q[1] * k1 + (int)q[2] * k2 + (int)q[3] * k3);
                 }
             }
         }
     }
     __syncthreads();
 
-    // (3) vertical pass, 4 consecutive columns per thread
-    const int qcols = kTW / 4;
-    for (int i = tid; i < 3 * kTH * qcols; i += 256) {
-        const int pl = i / (kTH * qcols);
-        const int rem = i - pl * (kTH * qcols);
-        const int ty = rem / qcols, q = rem - ty * qcols;
-        const int dy = dy0 + ty;
-        if (dy >= dy1) continue;
-        const int col = q * 4, dx = dx0 + col;
-        if (dx >= dx1) continue;
-        const int sr = p.yofs[dy] - 1 - sy_lo;
-        const short4 cy = p.ycoef[dy];
-        uint8_t* out = (pl == 0 ? p.y : (pl == 1 ? p.cr : p.cb)) + (size_t)(dy - p.plane_row0) * p.pitch + dx;
-        uint32_t packed = 0;
-        int v[4];
+    // (3) vertical pass: thread owns 4 consecutive columns (one 128-bit shared load per tap row) and
+    //     walks the tile rows; v = H0*b0 + (H1*b1 + (H2*b2 + H3*b3)), separate multiplies and adds
+    {
+        const int q = tid & 15, col = q * 4, dx = dx0 + col;
+        if (dx < dx1) {
+            const bool all_float = dx + 3 < p.simd_w && dx + 3 < dx1;
+            for (int ty = tid >> 4; ty < kTH; ty += 16) {
+                const int dy = dy0 + ty;
+                if (dy >= dy1) break;
+                const int sr = p.yofs[dy] - 1 - sy_lo;
+                const short4 cy = p.ycoef[dy];
+                const float sc = 1.0f / 4194304.0f;  // 2^-22, exact
+                const float b0 = __fmul_rn((float)cy.x, sc), b1 = __fmul_rn((float)cy.y, sc);
+                const float b2 = __fmul_rn((float)cy.z, sc), b3 = __fmul_rn((float)cy.w, sc);
+                const size_t o = (size_t)(dy - p.plane_row0) * p.pitch + dx;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const bool fpath = (dx + j) < p.simd_w;
-            v[j] = vertical_tap(sH[pl][sr][col + j], sH[pl][sr + 1][col + j], sH[pl][sr + 2][col + j],
-                                sH[pl][sr + 3][col + j], cy, fpath);
-            packed |= (uint32_t)v[j] << (8 * j);
-        }
-        if (dx + 3 < dx1) {
-            *reinterpret_cast<uint32_t*>(out) = packed;  // pitch and dx are multiples of 4
-        } else {
-            for (int j = 0; j < 4 && dx + j < dx1; j++) out[j] = (uint8_t)v[j];
+                for (int pl = 0; pl < 3; pl++) {
+                    const float4 h0 = *reinterpret_cast<const float4*>(&sH[pl][sr][col]);
+                    const float4 h1 = *reinterpret_cast<const float4*>(&sH[pl][sr + 1][col]);
+                    const float4 h2 = *reinterpret_cast<const float4*>(&sH[pl][sr + 2][col]);
+                    const float4 h3 = *reinterpret_cast<const float4*>(&sH[pl][sr + 3][col]);
+                    uint8_t* out = (pl == 0 ? p.y : (pl == 1 ? p.cr : p.cb)) + o;
+                    if (all_float) {
+#define VT(F) sat_u8_rn(__fadd_rn(__fmul_rn(h0.F, b0), __fadd_rn(__fmul_rn(h1.F, b1), __fadd_rn(__fmul_rn(h2.F, b2), __fmul_rn(h3.F, b3)))))
+                        *reinterpret_cast<uint32_t*>(out) = VT(x) | (VT(y) << 8) | (VT(z) << 16) | (VT(w) << 24);
+#undef VT
+                    } else {  // tile edge and/or cv::resize's integer scalar tail (last ow mod 8 columns)
+                        const float hh[4][4] = {{h0.x, h0.y, h0.z, h0.w}, {h1.x, h1.y, h1.z, h1.w}, {h2.x, h2.y, h2.z, h2.w}, {h3.x, h3.y, h3.z, h3.w}};
+                        for (int j = 0; j < 4 && dx + j < dx1; j++)
+                            out[j] = (uint8_t)vertical_tap(__float2int_rn(hh[0][j]), __float2int_rn(hh[1][j]), __float2int_rn(hh[2][j]),
+                                                           __float2int_rn(hh[3][j]), cy, (dx + j) < p.simd_w);
+                    }
+                }
+            }
         }
     }
 }
@@ -342,8 +360,61 @@ __global__ void __launch_bounds__(256) k_merge_ycc2bgr(const uint8_t* __restrict
     }
 }
 
+// 16 pixels per thread: three 128-bit plane loads, three 128-bit stores (needs 16-byte aligned rows)
+__global__ void __launch_bounds__(256) k_merge_ycc2bgr_v16(const uint8_t* __restrict__ y, const uint8_t* __restrict__ cr,
+                                                           const uint8_t* __restrict__ cb, size_t pitch, int w, int rows,
+                                                           int swapRB, uint8_t* __restrict__ dst, size_t dst_stride,
+                                                           int blocks_per_row) {
+    const int row = blockIdx.x / blocks_per_row;
+    const int g = (blockIdx.x - row * blocks_per_row) * blockDim.x + threadIdx.x;  // 16-pixel group
+    const int x = g * 16;
+    if (x >= w || row >= rows) return;
+    const size_t o = (size_t)row * pitch + x;
+    const uint4 vy = *reinterpret_cast<const uint4*>(y + o);
+    const uint4 vr = *reinterpret_cast<const uint4*>(cr + o);
+    const uint4 vb = *reinterpret_cast<const uint4*>(cb + o);
+    const uint32_t wy[4] = {vy.x, vy.y, vy.z, vy.w}, wr[4] = {vr.x, vr.y, vr.z, vr.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
+    uint32_t outw[12];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {   // 4 pixels -> 12 bytes -> 3 words
+        uint32_t px[12];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int B, G, R;
+            ycc_to_bgr((wy[k] >> (8 * j)) & 255, (wr[k] >> (8 * j)) & 255, (wb[k] >> (8 * j)) & 255, B, G, R);
+            px[3 * j] = (uint32_t)(swapRB ? R : B);
+            px[3 * j + 1] = (uint32_t)G;
+            px[3 * j + 2] = (uint32_t)(swapRB ? B : R);
+        }
+        outw[3 * k] = px[0] | (px[1] << 8) | (px[2] << 16) | (px[3] << 24);
+        outw[3 * k + 1] = px[4] | (px[5] << 8) | (px[6] << 16) | (px[7] << 24);
+        outw[3 * k + 2] = px[8] | (px[9] << 8) | (px[10] << 16) | (px[11] << 24);
+    }
+    uint8_t* d = dst + (size_t)row * dst_stride + 3 * (size_t)x;
+    if (x + 15 < w) {
+        uint4* d4 = reinterpret_cast<uint4*>(d);
+        d4[0] = make_uint4(outw[0], outw[1], outw[2], outw[3]);
+        d4[1] = make_uint4(outw[4], outw[5], outw[6], outw[7]);
+        d4[2] = make_uint4(outw[8], outw[9], outw[10], outw[11]);
+    } else {
+        const int n = (w - x) * 3;
+        for (int j = 0; j < n; j++) d[j] = (uint8_t)(outw[j >> 2] >> (8 * (j & 3)));
+    }
+}
+
 int launch_merge(Ctx* c, const MergeArgs& a) {
     if (a.rows <= 0 || a.w <= 0) return SRCNN_OK;
+    const bool wide = ((((uintptr_t)a.dst) | a.dst_stride | (uintptr_t)a.y | (uintptr_t)a.cr | (uintptr_t)a.cb | a.pitch) & 15) == 0 &&
+                      a.pitch >= align_up((size_t)a.w, 16);
+    if (wide) {
+        const int groups16 = (a.w + 15) / 16;
+        const int bpr16 = (groups16 + 255) / 256;
+        k_merge_ycc2bgr_v16<<<(unsigned)bpr16 * (unsigned)a.rows, 256, 0, c->stream>>>(a.y, a.cr, a.cb, a.pitch, a.w, a.rows,
+                                                                                    a.order == SRCNN_ORDER_RGB, a.dst, a.dst_stride, bpr16);
+        c->launches++;
+        SRCNN_CUDA(c, cudaGetLastError());
+        return SRCNN_OK;
+    }
     const int groups = (a.w + 3) / 4;
     const int bpr = (groups + 255) / 256;
     const unsigned grid = (unsigned)bpr * (unsigned)a.rows;

@@ -276,7 +276,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_srcnn_tc(const Params p) {
     const uint32_t rq0 = mb0 + 24;
     volatile uint32_t* tmem_slot = (volatile uint32_t*)(smem + kOffTmem);
 
+    // conv1 token: which pipeline currently streams its conv1 MMAs (0 = free, 1+pipe = held); tok[1] counts
+    // the issuer threads of the holder that are done
+    volatile unsigned int* tok = (volatile unsigned int*)(smem + kOffTmem + 8);
     if (tid == 0) {
+        tok[0] = 0;
+        tok[1] = 0;
         mbar_init(wbar, 1);
         for (int q = 0; q < 2; q++)
             for (int i = 0; i < 6; i++) mbar_init(sbase + kOffBar + 8 + q * 48 + i * 8, i == 0 ? 2 : (i < 3 ? 4 : 128));
@@ -329,6 +334,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_srcnn_tc(const Params p) {
                 for (int g = 0; g < G; g++) {
                     mbar_wait(rq0, q0, p.guard, 5);
                     q0 ^= 1;
+                    // One pipeline at a time streams conv1: the tensor queue is in order, so interleaving the two
+                    // pipelines' long conv1 batches puts them in lock-step (both wait, then both run epilogues
+                    // with the tensor pipe idle).  Serialising conv1 keeps them in anti-phase instead.
+                    {
+                        const long long tk0 = clock64();
+                        if (half_n == 0) {
+                            while (atomicCAS((unsigned int*)&tok[0], 0u, 1u + pipe) != 0u)
+                                if (clock64() - tk0 > 2000000000ll) { *p.guard = 9; __threadfence_system(); __trap(); }
+                        } else {
+                            while (tok[0] != 1u + pipe)
+                                if (clock64() - tk0 > 2000000000ll) { *p.guard = 10; __threadfence_system(); __trap(); }
+                        }
+                    }
                     tc_fence_after();
                     const int j = g >> 1, half = g & 1;
                     const uint32_t a0 = ring + (j & (kRingSlots - 1)) * kChunkBytes;
@@ -338,6 +356,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_srcnn_tc(const Params p) {
                     for (int i = 0; i < 9; i++)
                         mma_ss(dcol, smem_desc(a0 + i * 16, kChunkBytes, 128), smem_desc(b0 + i * kB1Tile, 4096, 128), idesc_f16(128), 1);
                     mma_commit(mb0);
+                    if (atomicAdd((unsigned int*)&tok[1], 1u) == 1u) {   // second issuer of this pipeline done: release
+                        tok[1] = 0;
+                        __threadfence_block();
+                        tok[0] = 0;
+                    }
                 }
             }
         }
