@@ -25,12 +25,14 @@
 //   * Biases ride on the tensor pipe too: one extra K=16 MMA whose A operand is a constant "ones" tile
 //     and whose B operand holds hi+lo FP16 halves of the FP32 bias (error < 1e-4), so the epilogues
 //     are pure ReLU+pack (cvt.rn.relu.f16x2.f32).
-//   * Two independent pipelines per CTA (one warpgroup each, one thread per TMEM lane; each owns 256
-//     TMEM columns, its own Y ring and barriers) ping-pong on the tensor pipe: while one runs its
-//     CUDA-core epilogue the other's MMAs execute.  A third warpgroup holds the two MMA-issuer
-//     threads, so a full tensor queue never stalls an epilogue.  Epilogue TMEM loads are software-
-//     pipelined (tcgen05.ld round trips are ~150 cycles).  The 163 KB of packed operands are fetched
-//     once per CTA with cp.async.bulk (TMA) and shared by both pipelines.
+//   * Two independent pipelines per CTA (one epilogue warpgroup each, one thread per TMEM lane; each
+//     owns 256 TMEM columns, its own Y ring and barriers) share the tensor pipe.  Inside a pipeline a
+//     group is two independently committed halves (2 columns each, 128 TMEM columns each) that the
+//     epilogue threads process interleaved, so the MMA -> epilogue -> MMA round trips of one half hide
+//     behind the CUDA-core work of the other.  Twelve dedicated issuer warps (a tcgen05.mma costs its
+//     issuing thread ~100+ cycles) keep the queue fed; epilogue TMEM loads are software-pipelined
+//     (tcgen05.ld round trips are ~150 cycles).  The 163 KB of packed operands are fetched once per
+//     CTA with cp.async.bulk (TMA) and shared by both pipelines.
 //
 // Executed tensor work per pixel: conv1 2*16*(9+1)*64 = 20 480 FLOP (K efficiency 9/16, +1 bias MMA),
 // conv2 5 120, conv3 2 048; algorithmic 16 064 FLOP/px is what bench.py reports against the roofline.
@@ -70,8 +72,8 @@ constexpr int kOffOnes = kOffBias2 + kBias2Bytes;
 constexpr int kOffRing = kOffW + kWeightBytes;
 constexpr int kOffHx = kOffRing + 2 * kRingBytes;
 constexpr int kOffBar = kOffHx + 2 * kHxBytes;    // 1 weight barrier + 2 x 3 pipeline barriers
-constexpr int kOffTmem = kOffBar + 24 * 8;
-constexpr int kThreads = 384;                    // 2 pipeline warpgroups + 1 warpgroup holding the 2 MMA issuers
+constexpr int kOffTmem = kOffBar + 32 * 8;
+constexpr int kThreads = 640;                    // 2 epilogue warpgroups + 3 warpgroups of MMA-issuer warps
 constexpr int kSmemBytes = kOffTmem + 64;
 static_assert(kWeightBytes % 64 == 0 && kSmemBytes <= 227 * 1024, "shared memory budget");
 
@@ -224,7 +226,7 @@ struct Params {
     int* guard;
     long long* dbg;        // optional timeline (SRCNN_TC_DEBUG=1): clock64 stamps of CTA 0
 };
-#define TL(slot) do { if (p.dbg && blockIdx.x == 0 && tp == 0 && g < 24) p.dbg[((pipe * 24 + g) * 8) + (slot)] = clock64(); } while (0)
+#define TL(slot) do { if (p.dbg && blockIdx.x == 0 && tp == 0 && g < 24) p.dbg[((pipe * 24 + g) * 16) + (slot)] = clock64(); } while (0)
 
 // One horizontal tap of conv3 (compile-time column D of the group, horizontal tap N, vertical tap M):
 // adds T to the output-window column it belongs to, plus the reference's clamped reads at the image's
@@ -255,36 +257,40 @@ __device__ __forceinline__ void taps_col(float (&acc)[8][5], const uint32_t* tv,
 }
 
 // ---------------------------------------------------------------------------------------------
-// the kernel: 12 warps.  Warpgroups 0 and 1 are two independent pipelines (one thread per TMEM lane:
-// 128 image rows each); warpgroup 2 holds the two MMA-issuer threads (warp 8 lane 0 -> pipeline 0,
-// warp 9 lane 0 -> pipeline 1).  A pipeline owns 256 TMEM columns, a Y ring, an exchange buffer and
-// six mbarriers; while it runs a CUDA-core epilogue the other pipeline's MMAs keep the tensor pipe busy.
+// the kernel: 20 warps.
+//   warps 0-3 / 4-7   : epilogue warpgroups of pipeline 0 / 1 (one thread per TMEM lane = image row)
+//   warps 8-19        : MMA issuers, lane 0 of each: per pipeline two conv1 issuers (one per half of the
+//                       group) and four conv2/conv3 issuers (one per output column).  A tcgen05.mma costs
+//                       its issuing thread ~100-120 cycles whatever its size, so issue is spread over
+//                       threads that do nothing else.
+// A group of 4 output columns is processed as two independently committed HALVES (columns 0,1 and 2,3),
+// each living in its own 128 TMEM columns.  The epilogue threads run the halves interleaved
+// (E1a E1b E2a E2b E3a E3b), so the MMA -> epilogue -> MMA round trips of one half hide behind the
+// CUDA-core work of the other; two such pipelines per SM share the tensor pipe.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads, 1) k_srcnn_tc(const Params p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const bool issuer = warp >= 8;
-    const int pipe = issuer ? (warp & 1) : (tid >> 7);   // independent pipeline
+    const int irole = issuer ? (warp - 8) % 6 : 0;        // 0,1: conv1 half a/b; 2..5: conv2+conv3 of column irole-2
+    const int pipe = issuer ? (warp - 8) / 6 : (tid >> 7);
     const int tp = tid & 127;        // thread within the pipeline = TMEM lane = image row R0 + tp
     const int quarter = warp & 3;    // TMEM lane quarter this warp may access
     const uint32_t sbase = smem_u32(smem);
     const uint32_t wbar = sbase + kOffBar;
-    // per pipeline: mb0..2 = "conv1/2/3 MMAs complete" (tcgen05.commit), rq0..2 = "operands of conv1/2/3
-    // are ready" (128 epilogue-thread arrivals each)
-    const uint32_t mb0 = sbase + kOffBar + 8 + pipe * 48, mb1 = mb0 + 8, mb2 = mb0 + 16;
-    const uint32_t rq0 = mb0 + 24;
+    // per pipeline, per half h: mb0[h], mb1[h], mb2[h] = "conv1/2/3 MMAs of the half complete" (tcgen05.commit);
+    // rq0[h], rq1[h], rq2[h] = "operands of conv1/2/3 of the half are ready" (128 epilogue arrivals)
+    const uint32_t bars = sbase + kOffBar + 8 + pipe * 96;
+    auto MB = [&](int stage, int h) { return bars + (uint32_t)(stage * 2 + h) * 8; };
+    auto RQ = [&](int stage, int h) { return bars + 48 + (uint32_t)(stage * 2 + h) * 8; };
     volatile uint32_t* tmem_slot = (volatile uint32_t*)(smem + kOffTmem);
 
-    // conv1 token: which pipeline currently streams its conv1 MMAs (0 = free, 1+pipe = held); tok[1] counts
-    // the issuer threads of the holder that are done
-    volatile unsigned int* tok = (volatile unsigned int*)(smem + kOffTmem + 8);
     if (tid == 0) {
-        tok[0] = 0;
-        tok[1] = 0;
         mbar_init(wbar, 1);
         for (int q = 0; q < 2; q++)
-            for (int i = 0; i < 6; i++) mbar_init(sbase + kOffBar + 8 + q * 48 + i * 8, i == 0 ? 2 : (i < 3 ? 4 : 128));
+            for (int i = 0; i < 12; i++)
+                mbar_init(sbase + kOffBar + 8 + q * 96 + i * 8, i < 2 ? 1 : (i < 6 ? 2 : 128));
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(smem_u32((const void*)tmem_slot), 512);
@@ -299,13 +305,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_srcnn_tc(const Params p) {
     }
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tm = tmem_base + pipe * 256;                         // this pipeline's 256 columns
-    const uint32_t tml = tm + ((uint32_t)(quarter * 32) << 16);         // + this warp's lane quarter
     const uint32_t ring = sbase + kOffRing + pipe * kRingBytes;
-    uint8_t* ring_p = smem + kOffRing + pipe * kRingBytes;
-    float* hx = (float*)(smem + kOffHx + pipe * kHxBytes);
-    const int pbar = 1 + pipe;                    // named barrier of the pipeline (128 threads)
-
-    mbar_wait(wbar, 0, p.guard, 1);
 
     const int W = p.W, H = p.H;
     const long long nworkers = (long long)gridDim.x * 2;
@@ -314,15 +314,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_srcnn_tc(const Params p) {
     const long long lin_end = p.total_groups * (wk + 1) / nworkers;
 
     if (issuer) {
-        // ---------------- conv1 issuers: two threads per pipeline, each owns one N=128 half of D1 ----------------
-        // (a tcgen05.mma costs its issuing thread ~100-120 cycles whatever N is -- tools/microbench/mma_rate2.cu --
-        //  so the ten conv1 MMAs are split over two threads, and the short conv2/conv3 batches are issued by
-        //  the four epilogue warps themselves, one output column each)
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");   // the three issuer warpgroups hand registers to the epilogues
         if ((tid & 31) == 0) {
-            const int half_n = (warp >> 1) & 1;          // warps 8,9 -> D1 columns [0,128); warps 10,11 -> [128,256)
-            const uint32_t dcol = tm + half_n * 128;
-            const uint32_t bofs = half_n * 2048;         // rows 128..255 of a [256][16] no-swizzle tile
-            uint32_t q0 = 0;
+            mbar_wait(wbar, 0, p.guard, 1);
+            uint32_t ph = 0;   // every request barrier completes exactly once per group
             while (lin < lin_end) {
                 const int band = (int)(lin / p.gpb);
                 const int gfirst = (int)(lin - (long long)band * p.gpb);
@@ -331,41 +326,57 @@ __global__ void __launch_bounds__(kThreads, 1) k_srcnn_tc(const Params p) {
                 const int s = gfirst * 4;
                 const int e = min(W, s + ng * 4);
                 const int G = (e - s + 3) / 4 + 1;
-                for (int g = 0; g < G; g++) {
-                    mbar_wait(rq0, q0, p.guard, 5);
-                    q0 ^= 1;
-                    // One pipeline at a time streams conv1: the tensor queue is in order, so interleaving the two
-                    // pipelines' long conv1 batches puts them in lock-step (both wait, then both run epilogues
-                    // with the tensor pipe idle).  Serialising conv1 keeps them in anti-phase instead.
-                    {
-                        const long long tk0 = clock64();
-                        if (half_n == 0) {
-                            while (atomicCAS((unsigned int*)&tok[0], 0u, 1u + pipe) != 0u)
-                                if (clock64() - tk0 > 2000000000ll) { *p.guard = 9; __threadfence_system(); __trap(); }
-                        } else {
-                            while (tok[0] != 1u + pipe)
-                                if (clock64() - tk0 > 2000000000ll) { *p.guard = 10; __threadfence_system(); __trap(); }
-                        }
-                    }
-                    tc_fence_after();
-                    const int j = g >> 1, half = g & 1;
-                    const uint32_t a0 = ring + (j & (kRingSlots - 1)) * kChunkBytes;
-                    const uint32_t b0 = sbase + kOffW + half * 9 * kB1Tile + bofs;
-                    mma_ss(dcol, smem_desc(sbase + kOffOnes, 2048, 128), smem_desc(sbase + kOffBias1 + bofs, 4096, 128), idesc_f16(128), 0);
+                if (irole < 2) {
+                    // ---- conv1 of one half: bias MMA + 9 Toeplitz MMAs (M128 N128 K16) into D1 of the half ----
+                    const int h = irole;
+                    const uint32_t dcol = tm + h * 128;
+                    const uint32_t bofs = h * 2048;   // rows 128..255 of a [256][16] no-swizzle tile
+                    for (int g = 0; g < G; g++) {
+                        mbar_wait(RQ(0, h), ph, p.guard, 5);
+                        ph ^= 1;
+                        tc_fence_after();
+                        const int j = g >> 1, half = g & 1;
+                        const uint32_t a0 = ring + (j & (kRingSlots - 1)) * kChunkBytes;
+                        const uint32_t b0 = sbase + kOffW + half * 9 * kB1Tile + bofs;
+                        mma_ss(dcol, smem_desc(sbase + kOffOnes, 2048, 128), smem_desc(sbase + kOffBias1 + bofs, 4096, 128), idesc_f16(128), 0);
 #pragma unroll
-                    for (int i = 0; i < 9; i++)
-                        mma_ss(dcol, smem_desc(a0 + i * 16, kChunkBytes, 128), smem_desc(b0 + i * kB1Tile, 4096, 128), idesc_f16(128), 1);
-                    mma_commit(mb0);
-                    if (atomicAdd((unsigned int*)&tok[1], 1u) == 1u) {   // second issuer of this pipeline done: release
-                        tok[1] = 0;
-                        __threadfence_block();
-                        tok[0] = 0;
+                        for (int i = 0; i < 9; i++)
+                            mma_ss(dcol, smem_desc(a0 + i * 16, kChunkBytes, 128), smem_desc(b0 + i * kB1Tile, 4096, 128), idesc_f16(128), 1);
+                        mma_commit(MB(0, h));
+                    }
+                } else {
+                    // ---- conv2 and conv3 of one output column d ----
+                    const int d = irole - 2, h = d >> 1, dl = d & 1;
+                    const uint32_t hb = tm + h * 128;
+                    for (int g = 0; g < G; g++) {
+                        // conv2: D2[d] = b2 + A1[d] (TMEM) x W2, K = 64 in 4 steps
+                        mbar_wait(RQ(1, h), ph, p.guard, 6);
+                        tc_fence_after();
+                        mma_ss(hb + 64 + dl * 32, smem_desc(sbase + kOffOnes, 2048, 128), smem_desc(sbase + kOffBias2, 512, 128), idesc_f16(32), 0);
+#pragma unroll
+                        for (int ks = 0; ks < 4; ks++)
+                            mma_ts(hb + 64 + dl * 32, hb + dl * 32 + ks * 8, smem_desc(sbase + kImgB2 + ks * 1024, 512, 128), idesc_f16(32), 1);
+                        mma_commit(MB(1, h));
+                        // conv3 tap GEMM: T[d][tap] = A2[d] (TMEM) x W3, K = 32 in 2 steps
+                        mbar_wait(RQ(2, h), ph, p.guard, 7);
+                        ph ^= 1;
+                        tc_fence_after();
+#pragma unroll
+                        for (int ks = 0; ks < 2; ks++)
+                            mma_ts(hb + dl * 32, hb + 64 + dl * 16 + ks * 8, smem_desc(sbase + kImgB3 + ks * 1024, 512, 128), idesc_f16(32), ks > 0);
+                        mma_commit(MB(2, h));
                     }
                 }
             }
         }
     } else {
-    uint32_t ph0 = 0, ph1 = 0, ph2 = 0;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 176;");
+    const uint32_t tml = tm + ((uint32_t)(quarter * 32) << 16);         // + this warp's lane quarter
+    uint8_t* ring_p = smem + kOffRing + pipe * kRingBytes;
+    float* hx = (float*)(smem + kOffHx + pipe * kHxBytes);
+    const int pbar = 1 + pipe;                    // named barrier of the pipeline (128 threads)
+    mbar_wait(wbar, 0, p.guard, 1);
+    uint32_t ph = 0;   // every completion barrier fires exactly once per group
     while (lin < lin_end) {
         // ---- one segment: band `band`, output columns [s, e) ----
         const int band = (int)(lin / p.gpb);
@@ -432,11 +443,51 @@ __global__ void __launch_bounds__(kThreads, 1) k_srcnn_tc(const Params p) {
                 store_row(q, 128 + tp, lo, hi);
             }
         };
+        // E1 of one half: D1 (2 columns x 64 ch fp32 = 128 TMEM columns) -> ReLU, FP16 -> A1 (64 columns, in place).
+        // Four 32-column chunks, software-pipelined: chunk k+1 is in flight while chunk k is packed.
+        auto e1_half = [&](uint32_t hb) {
+            uint32_t va[32], vb[32], r[16];
+            tmem_ld32(hb, va);
+            tc_wait_ld();
+            tmem_ld32(hb + 32, vb);
+#pragma unroll
+            for (int c = 0; c < 16; c++) r[c] = relu_pack_f16x2(__uint_as_float(va[2 * c]), __uint_as_float(va[2 * c + 1]));
+            tmem_st16(hb, r);
+            tc_wait_ld();
+            tmem_ld32(hb + 64, va);
+#pragma unroll
+            for (int c = 0; c < 16; c++) r[c] = relu_pack_f16x2(__uint_as_float(vb[2 * c]), __uint_as_float(vb[2 * c + 1]));
+            tmem_st16(hb + 16, r);
+            tc_wait_ld();
+            tmem_ld32(hb + 96, vb);
+#pragma unroll
+            for (int c = 0; c < 16; c++) r[c] = relu_pack_f16x2(__uint_as_float(va[2 * c]), __uint_as_float(va[2 * c + 1]));
+            tmem_st16(hb + 32, r);
+            tc_wait_ld();
+#pragma unroll
+            for (int c = 0; c < 16; c++) r[c] = relu_pack_f16x2(__uint_as_float(vb[2 * c]), __uint_as_float(vb[2 * c + 1]));
+            tmem_st16(hb + 48, r);
+        };
+        // E2 of one half: D2 (2 columns x 32 ch at [hb+64, hb+128)) -> ReLU, FP16 -> A2 (in place at [hb+64, hb+96))
+        auto e2_half = [&](uint32_t hb) {
+            uint32_t va[32], vb[32], r[16];
+            tmem_ld32(hb + 64, va);
+            tc_wait_ld();
+            tmem_ld32(hb + 96, vb);
+#pragma unroll
+            for (int c = 0; c < 16; c++) r[c] = relu_pack_f16x2(__uint_as_float(va[2 * c]), __uint_as_float(va[2 * c + 1]));
+            tmem_st16(hb + 64, r);
+            tc_wait_ld();
+#pragma unroll
+            for (int c = 0; c < 16; c++) r[c] = relu_pack_f16x2(__uint_as_float(vb[2 * c]), __uint_as_float(vb[2 * c + 1]));
+            tmem_st16(hb + 80, r);
+        };
 
         stage_chunk_now(0);
         stage_chunk_now(1);
         fence_proxy_async();
-        mbar_arrive(rq0);   // Y chunks 0,1 staged (and the previous segment is fully drained): conv1(0) may issue
+        mbar_arrive(RQ(0, 0));   // Y chunks 0,1 staged (and the previous segment is fully drained): conv1(0) may issue
+        mbar_arrive(RQ(0, 1));
 
         // horizontal-tap accumulators: window column cw <-> image column t0-2+cw; columns 0..3 finish in the
         // current group, 4..7 are partial and slide down afterwards.  [.][m]: vertical tap
@@ -455,39 +506,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_srcnn_tc(const Params p) {
                 fetch_row(yrow0, s - 6 + 8 * (j + 2), pre0, pre1);
                 if (tp < 8) fetch_row(yrow1, s - 6 + 8 * (j + 2), pre2, pre3);
             }
-            // ---------------- E1: D1 -> ReLU, FP16 -> A1 (in place, columns [0,128)) ----------------
-            // software-pipelined: the TMEM loads of column d+1 are in flight while column d is packed
-            mbar_wait(mb0, ph0, p.guard, 2);
+            const int t0 = s - 2 + 4 * g;  // first T column of this group
+            // ---------------- E1, half a then half b ----------------
+            mbar_wait(MB(0, 0), ph, p.guard, 2);
             TL(1);
-            ph0 ^= 1;
             tc_fence_after();
-            {
-                uint32_t va[64], vb[64], r[32];
-                tmem_ld32(tml, va);
-                tmem_ld32(tml + 32, va + 32);
-                tc_wait_ld();
-                tmem_ld32(tml + 64, vb);
-                tmem_ld32(tml + 96, vb + 32);
-#pragma unroll
-                for (int c = 0; c < 32; c++) r[c] = relu_pack_f16x2(__uint_as_float(va[2 * c]), __uint_as_float(va[2 * c + 1]));
-                tmem_st32(tml, r);
-                tc_wait_ld();
-                tmem_ld32(tml + 128, va);
-                tmem_ld32(tml + 160, va + 32);
-#pragma unroll
-                for (int c = 0; c < 32; c++) r[c] = relu_pack_f16x2(__uint_as_float(vb[2 * c]), __uint_as_float(vb[2 * c + 1]));
-                tmem_st32(tml + 32, r);
-                tc_wait_ld();
-                tmem_ld32(tml + 192, vb);
-                tmem_ld32(tml + 224, vb + 32);
-#pragma unroll
-                for (int c = 0; c < 32; c++) r[c] = relu_pack_f16x2(__uint_as_float(va[2 * c]), __uint_as_float(va[2 * c + 1]));
-                tmem_st32(tml + 64, r);
-                tc_wait_ld();
-#pragma unroll
-                for (int c = 0; c < 32; c++) r[c] = relu_pack_f16x2(__uint_as_float(vb[2 * c]), __uint_as_float(vb[2 * c + 1]));
-                tmem_st32(tml + 96, r);
-            }
+            e1_half(tml);
             if (prefetch) {
                 store_row(j + 2, tp, pre0, pre1);
                 if (tp < 8) store_row(j + 2, 128 + tp, pre2, pre3);
@@ -495,65 +519,37 @@ __global__ void __launch_bounds__(kThreads, 1) k_srcnn_tc(const Params p) {
             }
             tc_wait_st();
             tc_fence_before();
+            mbar_arrive(RQ(1, 0));   // A1 of half a complete for my lane -> its two conv2 issuers start when all 128 arrived
             TL(2);
-            named_bar(pbar, 128);   // A1 complete for all 128 lanes
-            if ((tid & 31) == 0) {  // conv2 of column d = this warp: D2[d] = b2 + A1[d] (TMEM) x W2, K = 64 in 4 steps
-                tc_fence_after();
-                const int d = quarter;
-                mma_ss(tm + 128 + d * 32, smem_desc(sbase + kOffOnes, 2048, 128), smem_desc(sbase + kOffBias2, 512, 128), idesc_f16(32), 0);
-#pragma unroll
-                for (int ks = 0; ks < 4; ks++)
-                    mma_ts(tm + 128 + d * 32, tm + d * 32 + ks * 8, smem_desc(sbase + kImgB2 + ks * 1024, 512, 128), idesc_f16(32), 1);
-                mma_commit(mb1);
-            }
-            __syncwarp();
-            // ---------------- E2: D2 -> ReLU, FP16 -> A2 (in place, columns [128,192)) ----------------
-            mbar_wait(mb1, ph1, p.guard, 3);
+            mbar_wait(MB(0, 1), ph, p.guard, 2);
             TL(3);
-            ph1 ^= 1;
             tc_fence_after();
-            {
-                uint32_t va[32], vb[32], r[16];
-                tmem_ld32(tml + 128, va);
-                tc_wait_ld();
-                tmem_ld32(tml + 160, vb);
-#pragma unroll
-                for (int c = 0; c < 16; c++) r[c] = relu_pack_f16x2(__uint_as_float(va[2 * c]), __uint_as_float(va[2 * c + 1]));
-                tmem_st16(tml + 128, r);
-                tc_wait_ld();
-                tmem_ld32(tml + 192, va);
-#pragma unroll
-                for (int c = 0; c < 16; c++) r[c] = relu_pack_f16x2(__uint_as_float(vb[2 * c]), __uint_as_float(vb[2 * c + 1]));
-                tmem_st16(tml + 144, r);
-                tc_wait_ld();
-                tmem_ld32(tml + 224, vb);
-#pragma unroll
-                for (int c = 0; c < 16; c++) r[c] = relu_pack_f16x2(__uint_as_float(va[2 * c]), __uint_as_float(va[2 * c + 1]));
-                tmem_st16(tml + 160, r);
-                tc_wait_ld();
-#pragma unroll
-                for (int c = 0; c < 16; c++) r[c] = relu_pack_f16x2(__uint_as_float(vb[2 * c]), __uint_as_float(vb[2 * c + 1]));
-                tmem_st16(tml + 176, r);
-            }
+            e1_half(tml + 128);
             tc_wait_st();
             tc_fence_before();
+            mbar_arrive(RQ(1, 1));
             TL(4);
-            named_bar(pbar, 128);   // A2 complete for all 128 lanes
-            if ((tid & 31) == 0) {  // conv3 tap GEMM of column d = this warp: T[d] = A2[d] (TMEM) x W3, K = 32 in 2 steps
-                tc_fence_after();
-                const int d = quarter;
-#pragma unroll
-                for (int ks = 0; ks < 2; ks++)
-                    mma_ts(tm + d * 32, tm + 128 + d * 16 + ks * 8, smem_desc(sbase + kImgB3 + ks * 1024, 512, 128), idesc_f16(32), ks > 0);
-                mma_commit(mb2);
-            }
-            __syncwarp();
-            // ---------------- E3a: horizontal taps in registers ----------------
-            mbar_wait(mb2, ph2, p.guard, 4);
+            // ---------------- E2, half a then half b ----------------
+            mbar_wait(MB(1, 0), ph, p.guard, 3);
             TL(5);
-            ph2 ^= 1;
             tc_fence_after();
-            const int t0 = s - 2 + 4 * g;  // first T column of this group
+            e2_half(tml);
+            tc_wait_st();
+            tc_fence_before();
+            mbar_arrive(RQ(2, 0));
+            TL(6);
+            mbar_wait(MB(1, 1), ph, p.guard, 3);
+            TL(7);
+            tc_fence_after();
+            e2_half(tml + 128);
+            tc_wait_st();
+            tc_fence_before();
+            mbar_arrive(RQ(2, 1));
+            TL(8);
+            // ---------------- E3a: horizontal taps in registers, half a (T columns 0,1) then half b (2,3) ----------------
+            mbar_wait(MB(2, 0), ph, p.guard, 4);
+            TL(9);
+            tc_fence_after();
             {
                 uint32_t ta[32], tb[32];
                 tmem_ld32(tml, ta);
@@ -561,14 +557,26 @@ __global__ void __launch_bounds__(kThreads, 1) k_srcnn_tc(const Params p) {
                 tmem_ld32(tml + 32, tb);
                 if (t0 >= 0 && t0 < W) taps_col<0>(acc, ta, t0 == 0, t0 == W - 1);
                 tc_wait_ld();
-                tmem_ld32(tml + 64, ta);
                 if (t0 + 1 >= 0 && t0 + 1 < W) taps_col<1>(acc, tb, t0 + 1 == 0, t0 + 1 == W - 1);
+            }
+            tc_fence_before();
+            if (g + 1 < G) mbar_arrive(RQ(0, 0));   // T of half a fully read: its D1 region is reusable, next Y chunk is staged
+            TL(10);
+            mbar_wait(MB(2, 1), ph, p.guard, 4);
+            TL(11);
+            tc_fence_after();
+            {
+                uint32_t ta[32], tb[32];
+                tmem_ld32(tml + 128, ta);
                 tc_wait_ld();
-                tmem_ld32(tml + 96, tb);
+                tmem_ld32(tml + 128 + 32, tb);
                 if (t0 + 2 >= 0 && t0 + 2 < W) taps_col<2>(acc, ta, t0 + 2 == 0, t0 + 2 == W - 1);
                 tc_wait_ld();
                 if (t0 + 3 >= 0 && t0 + 3 < W) taps_col<3>(acc, tb, t0 + 3 == 0, t0 + 3 == W - 1);
             }
+            tc_fence_before();
+            if (g + 1 < G) mbar_arrive(RQ(0, 1));
+            ph ^= 1;
             // vertical taps cross lanes: publish the 4 finished columns
 #pragma unroll
             for (int m = 0; m < 5; m++)
@@ -578,11 +586,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_srcnn_tc(const Params p) {
             for (int a = 0; a < 4; a++)   // slide the window: the 4 partial columns become the next group's first 4
 #pragma unroll
                 for (int m = 0; m < 5; m++) { acc[a][m] = acc[a + 4][m]; acc[a + 4][m] = 0.f; }
-            tc_fence_before();
-            TL(6);
-            if (g + 1 < G) mbar_arrive(rq0);   // T fully read (D1 region reusable), next Y chunk staged
+            TL(12);
             named_bar(pbar, 128);              // hx visible to the whole pipeline
-            TL(7);
+            TL(13);
             // ---------------- E3b: vertical taps, bias, truncate, clamp, store (4 columns per thread) ----------------
             {
                 const int row = R0 + tp;
@@ -615,6 +621,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_srcnn_tc(const Params p) {
                     }
                 }
             }
+            TL(14);
         }
         // segment done: every MMA of this pipeline has been waited for; the hx reads of the last group
         // finish before the next segment's first hx write (conv3 of the next group needs all 128 arrivals)
@@ -792,10 +799,10 @@ int launch_cnn_tc(Ctx* c, const CnnArgs& a) {
     p.dbg = nullptr;
     if (getenv("SRCNN_TC_DEBUG")) {
         if (!c->work_buf.p) {
-            int rc = ensure(c, c->work_buf, 2 * 24 * 8 * sizeof(long long));
+            int rc = ensure(c, c->work_buf, 2 * 24 * 16 * sizeof(long long));
             if (rc) return rc;
         }
-        cudaMemsetAsync(c->work_buf.p, 0, 2 * 24 * 8 * sizeof(long long), c->stream);
+        cudaMemsetAsync(c->work_buf.p, 0, 2 * 24 * 16 * sizeof(long long), c->stream);
         p.dbg = (long long*)c->work_buf.p;
     }
     // one persistent CTA per SM; fewer when the image is too small to give every warpgroup ~8 groups
@@ -814,7 +821,7 @@ extern "C" __attribute__((visibility("default"))) int srcnn_debug_tc_timeline(sr
     if (!c || !c->work_buf.p) return SRCNN_E_ARG;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    return cudaMemcpy(out, c->work_buf.p, 2 * 24 * 8 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? SRCNN_OK : SRCNN_E_CUDA;
+    return cudaMemcpy(out, c->work_buf.p, 2 * 24 * 16 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? SRCNN_OK : SRCNN_E_CUDA;
 }
 
 // test hook (not part of the stable ABI; exported for tests/test_tc_primitives.py)

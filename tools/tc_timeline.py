@@ -10,16 +10,13 @@ out = torch.zeros_like(y)
 for _ in range(3):
     eng.stage_cnn(y, out)
 eng.sync()
-buf = (C.c_longlong * (2 * 24 * 8))()
+buf = (C.c_longlong * (2 * 24 * 16))()
 eng.L.srcnn_debug_tc_timeline.argtypes = [C.c_void_p, C.c_void_p]
 assert eng.L.srcnn_debug_tc_timeline(eng.ctx, buf) == 0
-a = np.array(buf[:]).reshape(2, 24, 8)
-names = ["top", "c1done", "E1done", "c2done", "E2done", "c3done", "E3a done"]
+a = np.array(buf[:]).reshape(2, 24, 16)
+names = ["c1a", "E1a", "c1b", "E1b", "c2a", "E2a", "c2b", "E2b", "c3a", "E3a", "c3b", "E3b'", "bar", "E3b"]
 for pipe in range(2):
     print("pipe", pipe)
-    for g in range(2, 12):
+    for g in range(2, 10):
         r = a[pipe, g]
-        prev = a[pipe, g - 1][6]
-        pb = a[pipe, g - 1][7]
-        print(" g%2d" % g, "bar %5d E3b %5d | fetch+c1wait %5d E1 %5d c2wait %5d E2 %5d c3wait %5d E3a %5d | total %5d" % (
-            pb - prev, r[0] - pb, r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] - r[3], r[5] - r[4], r[6] - r[5], r[6] - prev))
+        print(" g%2d " % g + " ".join("%s %4d" % (names[k], r[k + 1] - r[k]) for k in range(14)) + " | total %5d" % (r[14] - r[0]))
