@@ -225,6 +225,9 @@ int srcnn_destroy(srcnn_ctx* c) {
     for (DevBuf* b : {&c->plane_buf, &c->act2_buf, &c->src_buf, &c->dst_buf, &c->work_buf})
         if (b->p) cudaFree(b->p);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->pipe_events) cudaEventDestroy(e);
+    if (c->s_in) cudaStreamDestroy(c->s_in);
+    if (c->s_out) cudaStreamDestroy(c->s_out);
     if (c->h_work) cudaFreeHost(c->h_work);
     if (c->d_params) cudaFree(c->d_params);
     if (c->h_guard) cudaFreeHost(c->h_guard);
@@ -357,17 +360,54 @@ int srcnn_process_batch_host(srcnn_ctx* c, const uint8_t* src, int n, int w, int
     if (rc) return rc;
     uint8_t* ds = (uint8_t*)c->src_buf.p;
     uint8_t* dd = (uint8_t*)c->dst_buf.p;
+    // Three-stage pipeline on three streams: copy-in (H2D), compute (the context stream), copy-out (D2H).
+    // A unit is one row band of one frame (a single frame is cut into bands so that its D2H -- 4x the H2D
+    // bytes at x2 -- overlaps the kernels of the next band; frames of a batch overlap the same way).
+    if (!c->s_in) {
+        SRCNN_CUDA(c, cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+        SRCNN_CUDA(c, cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+    }
+    auto event_at = [&](size_t i, cudaEvent_t* e) -> int {
+        while (c->pipe_events.size() <= i) {
+            cudaEvent_t ev;
+            SRCNN_CUDA(c, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            c->pipe_events.push_back(ev);
+        }
+        *e = c->pipe_events[i];
+        return SRCNN_OK;
+    };
+    const int bands = (n == 1 && oh >= 1024) ? 4 : 1;
+    cudaEvent_t ev_start;
+    if ((rc = event_at(0, &ev_start))) return rc;
     for (int f0 = 0; f0 < n; f0 += chunk) {
         const int m = std::min(chunk, n - f0);
-        for (int f = 0; f < m; f++)
-            SRCNN_CUDA(c, cudaMemcpy2DAsync(ds + f * s_frame, s_row, src + (size_t)(f0 + f) * src_frame_stride, src_stride,
-                                            (size_t)w * 3, h, cudaMemcpyHostToDevice, c->stream));
+        size_t ei = 1;
+        // everything queued earlier on the compute stream (previous calls, tap-table uploads) precedes the copies
+        SRCNN_CUDA(c, cudaEventRecord(ev_start, c->stream));
+        SRCNN_CUDA(c, cudaStreamWaitEvent(c->s_in, ev_start, 0));
+        SRCNN_CUDA(c, cudaStreamWaitEvent(c->s_out, ev_start, 0));
         for (int f = 0; f < m; f++) {
-            rc = process_rows(c, ds + f * s_frame, w, h, s_row, 0, h, order, scale, ow, oh, 0, oh, dd + f * d_frame, d_row);
-            if (rc) return rc;
-            SRCNN_CUDA(c, cudaMemcpy2DAsync(dst + (size_t)(f0 + f) * dst_frame_stride, dst_stride, dd + f * d_frame, d_row,
-                                            (size_t)ow * 3, oh, cudaMemcpyDeviceToHost, c->stream));
+            cudaEvent_t ev_in;
+            if ((rc = event_at(ei++, &ev_in))) return rc;
+            SRCNN_CUDA(c, cudaMemcpy2DAsync(ds + f * s_frame, s_row, src + (size_t)(f0 + f) * src_frame_stride, src_stride,
+                                            (size_t)w * 3, h, cudaMemcpyHostToDevice, c->s_in));
+            SRCNN_CUDA(c, cudaEventRecord(ev_in, c->s_in));
+            SRCNN_CUDA(c, cudaStreamWaitEvent(c->stream, ev_in, 0));
+            for (int bi = 0; bi < bands; bi++) {
+                const int r0 = (int)((long long)oh * bi / bands), r1 = (int)((long long)oh * (bi + 1) / bands);
+                rc = process_rows(c, ds + f * s_frame, w, h, s_row, 0, h, order, scale, ow, oh, r0, r1,
+                                  dd + f * d_frame + (size_t)r0 * d_row, d_row);
+                if (rc) return rc;
+                cudaEvent_t ev_done;
+                if ((rc = event_at(ei++, &ev_done))) return rc;
+                SRCNN_CUDA(c, cudaEventRecord(ev_done, c->stream));
+                SRCNN_CUDA(c, cudaStreamWaitEvent(c->s_out, ev_done, 0));
+                SRCNN_CUDA(c, cudaMemcpy2DAsync(dst + (size_t)(f0 + f) * dst_frame_stride + (size_t)r0 * dst_stride, dst_stride,
+                                                dd + f * d_frame + (size_t)r0 * d_row, d_row, (size_t)ow * 3, r1 - r0,
+                                                cudaMemcpyDeviceToHost, c->s_out));
+            }
         }
+        SRCNN_CUDA(c, cudaStreamSynchronize(c->s_out));
         SRCNN_CUDA(c, cudaStreamSynchronize(c->stream));
         rc = check_guard(c);
         if (rc) return rc;

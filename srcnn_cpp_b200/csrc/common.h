@@ -83,6 +83,10 @@ struct Ctx {
     TapTable taps[8];
     unsigned long long tap_clock = 0;
 
+    // host-buffer pipeline (srcnn_process_batch_host): copy-in / copy-out streams and their events
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    std::vector<cudaEvent_t> pipe_events;
+
     // optional per-stage device timing (srcnn_profile_*): 4 events per process call
     bool profiling = false;
     std::vector<cudaEvent_t> ev_pool;
