@@ -98,6 +98,11 @@ class ClockSampler(threading.Thread):
 def cpu_reference_runner():
     from oracle.oracle import Oracle, RefLib, cv2_pipeline
     try:
+        import cv2
+        cv2.setNumThreads(os.cpu_count() or 1)
+    except Exception:
+        pass
+    try:
         ref = RefLib("O3")
         kind, threads = "reference", ref.threads()
 
@@ -305,6 +310,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
+        if rank == 0:
+            # torchrun exports OMP_NUM_THREADS=1; the CPU arm must use every host core it can (set before libgomp loads)
+            os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
         run_reference_arm(args, rank, world)
         return
     if world == 1 and args.gpus > 1:
