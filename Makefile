@@ -28,10 +28,11 @@ $(OBJ)/libsrcnn.o: srcnn_cpp_b200/cli/libsrcnn.cpp include/libsrcnn.h include/sr
 	@mkdir -p $(OBJ)
 	$(HOSTCXX) -std=c++17 -O2 -fPIC -fvisibility=hidden -c $< -o $@
 
-bin/srcnn: srcnn_cpp_b200/cli/srcnn_main.cpp srcnn_cpp_b200/cli/image_io.cpp srcnn_cpp_b200/cli/image_io.h $(LIB)
+bin/srcnn: srcnn_cpp_b200/cli/srcnn_main.cpp srcnn_cpp_b200/cli/image_io.cpp srcnn_cpp_b200/cli/jpeg_io.cpp srcnn_cpp_b200/cli/image_io.h $(LIB)
 	@mkdir -p bin
-	$(HOSTCXX) -std=c++17 -O2 srcnn_cpp_b200/cli/srcnn_main.cpp srcnn_cpp_b200/cli/image_io.cpp -o $@ \
-	    -Lsrcnn_cpp_b200 -lsrcnn_b200 -lz -lpthread -Wl,-rpath,'$$ORIGIN/../srcnn_cpp_b200'
+	$(HOSTCXX) -std=c++17 -O2 -I/usr/local/cuda/include srcnn_cpp_b200/cli/srcnn_main.cpp srcnn_cpp_b200/cli/image_io.cpp \
+	    srcnn_cpp_b200/cli/jpeg_io.cpp -o $@ -Lsrcnn_cpp_b200 -lsrcnn_b200 -L/usr/local/cuda/lib64 -lnvjpeg_static -lculibos -lcudart_static \
+	    -ldl -lrt -lz -lpthread -Wl,-rpath,'$$ORIGIN/../srcnn_cpp_b200'
 
 $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -shared -ccbin $(HOSTCXX) -Xcompiler -fPIC -o $@ $(OBJS) -lcuda

@@ -7,6 +7,9 @@
 #include <cstdlib>
 #include <cstring>
 
+bool jpeg_decode(const std::vector<uint8_t>& file, ImageBGR* out, std::string* err);   // jpeg_io.cpp (nvJPEG)
+bool jpeg_encode(const ImageBGR& img, std::vector<uint8_t>* file, std::string* err);
+
 namespace {
 
 bool read_file(const std::string& path, std::vector<uint8_t>* buf) {
@@ -176,7 +179,8 @@ bool image_read(const std::string& path, ImageBGR* out, std::string* err) {
     if (!read_file(path, &f)) { *err = "cannot read file"; return false; }
     if (f.size() >= 8 && f[0] == 0x89 && f[1] == 'P') return png_decode(f, out, err);
     if (f.size() >= 2 && f[0] == 'P' && (f[1] == '5' || f[1] == '6')) return pnm_decode(f, out, err);
-    *err = "unsupported image format (PNG and binary PPM/PGM are supported)";
+    if (f.size() >= 3 && f[0] == 0xff && f[1] == 0xd8 && f[2] == 0xff) return jpeg_decode(f, out, err);
+    *err = "unsupported image format (PNG, JPEG and binary PPM/PGM are supported)";
     return false;
 }
 
@@ -190,8 +194,10 @@ bool image_write(const std::string& path, const ImageBGR& img, std::string* err)
         for (size_t i = 0; i < (size_t)img.w * img.h; i++) { file.push_back(img.px[3 * i + 2]); file.push_back(img.px[3 * i + 1]); file.push_back(img.px[3 * i]); }
     } else if (e == ".png" || e.empty()) {
         if (!png_encode(img, &file)) { *err = "PNG encode failed"; return false; }
+    } else if (e == ".jpg" || e == ".jpeg") {
+        if (!jpeg_encode(img, &file, err)) return false;
     } else {
-        *err = "unsupported output format '" + e + "' (use .png or .ppm)";
+        *err = "unsupported output format '" + e + "' (use .png, .jpg or .ppm)";
         return false;
     }
     FILE* f = fopen(path.c_str(), "wb");

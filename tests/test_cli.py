@@ -73,3 +73,21 @@ def test_process_srcnn_library_entry(oracle):
     rgba = np.dstack([rgb, np.full((20, 26), 200, np.uint8)])
     assert fn(np.ascontiguousarray(rgba).ctypes.data, 26, 20, 4, C.c_float(2.0), C.byref(out), C.byref(sz)) == 0
     assert sz.value == 52 * 40 * 4
+
+
+@pytest.mark.gpu
+def test_jpeg_in_and_out(tmp_path, oracle):
+    """README.md:96-100 usage: ./bin/srcnn ./Pictures/test.jpg -> test_resized.jpg (JPEG through nvJPEG; file
+    codecs are outside the parity contract, so this checks geometry and a PSNR against the oracle on the
+    cv2-decoded input)."""
+    import cv2
+    img = cv2.imread(os.path.join(ROOT, "tests", "golden", "butterfly.png"))[:96, :128]
+    src = str(tmp_path / "t.jpg")
+    cv2.imwrite(src, img, [cv2.IMWRITE_JPEG_QUALITY, 95])
+    r = _run("--noverbose", src)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = cv2.imread(str(tmp_path / "t_resized.jpg"))
+    assert out is not None and out.shape == (192, 256, 3)
+    want = oracle.pipeline(cv2.imread(src), 2.0)
+    mse = np.mean((out.astype(np.float64) - want.astype(np.float64)) ** 2)
+    assert 10 * np.log10(255.0 ** 2 / mse) > 30.0
