@@ -128,6 +128,14 @@ int srcnn_stage_conv99x11_fp32_device(srcnn_ctx* ctx, const uint8_t* d_y, int w,
 int srcnn_stage_merge_device(srcnn_ctx* ctx, const uint8_t* d_y, const uint8_t* d_cr, const uint8_t* d_cb,
                              int w, int h, size_t plane_pitch, int order, uint8_t* d_dst, size_t dst_stride);
 
+/* ---- optional: frawscale-compatible float-plane resize --------------------------- */
+/* FRAWResizeEngine::scale (src/frawscale.h:160-161, src/frawscale.cpp:162-286) on device float planes (tight
+ * rows).  filter: 0 = Box, 1 = Bilinear, 2 = Bicubic (Mitchell B = C = 1/3, the reference default).  Not used by
+ * the bin/srcnn path (the reference never calls frawscale either); bit-identical to the compiled reference. */
+enum { SRCNN_FRAW_BOX = 0, SRCNN_FRAW_BILINEAR = 1, SRCNN_FRAW_BICUBIC = 2 };
+int srcnn_fraw_scale_device(srcnn_ctx* ctx, const float* d_src, unsigned src_w, unsigned src_h, unsigned dst_w,
+                            unsigned dst_h, float* d_dst, int filter);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -208,3 +208,31 @@ def cv2_pipeline(bgr, scale, cnn, stages=False):
     if stages:
         return out, dict(up_y=up[0], up_cr=up[1], up_cb=up[2], cnn_y=y2)
     return out
+
+
+class FrawRef:
+    """The reference's own float resampler, FRAWResizeEngine::scale (src/frawscale.cpp:162-286), compiled
+    unmodified into oracle/_ref/libfraw.so (oracle/fraw_wrap.cpp).  filter: 0 box, 1 bilinear, 2 bicubic."""
+
+    def __init__(self):
+        path = os.path.join(_HERE, "_ref", "libfraw.so")
+        if not os.path.exists(path):
+            if os.path.exists("/root/reference/src/frawscale.cpp"):
+                build()
+            else:
+                raise FileNotFoundError(path + " (built only where /root/reference exists)")
+        self.lib = C.CDLL(path)
+        self.lib.ref_fraw_scale.restype = C.c_uint
+        self.lib.ref_fraw_scale.argtypes = [_f32p, C.c_uint, C.c_uint, C.c_uint, C.c_uint, _f32p, C.c_int]
+
+    @staticmethod
+    def available():
+        return os.path.exists(os.path.join(_HERE, "_ref", "libfraw.so")) or os.path.exists("/root/reference/src/frawscale.cpp")
+
+    def scale(self, src, dw, dh, filter=2):
+        src = np.ascontiguousarray(src, dtype=np.float32)
+        sh, sw = src.shape
+        dst = np.zeros((dh, dw), np.float32)
+        n = self.lib.ref_fraw_scale(_ptr(src, _f32p), sw, sh, dw, dh, _ptr(dst, _f32p), int(filter))
+        assert n != 0
+        return dst

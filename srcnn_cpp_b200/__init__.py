@@ -37,6 +37,7 @@ ABI_SYMBOLS = [
     "srcnn_process_host", "srcnn_process_device", "srcnn_process_batch_device", "srcnn_process_batch_host",
     "srcnn_band_src_rows", "srcnn_process_band_device", "srcnn_stage_color_bicubic_device",
     "srcnn_stage_cnn_device", "srcnn_stage_conv99x11_fp32_device", "srcnn_stage_merge_device",
+    "srcnn_fraw_scale_device",
 ]
 
 
@@ -91,6 +92,7 @@ def load_library():
     L.srcnn_stage_cnn_device.argtypes = [vp, C.c_int, u8p, C.c_int, C.c_int, sz, u8p, sz]
     L.srcnn_stage_conv99x11_fp32_device.argtypes = [vp, u8p, C.c_int, C.c_int, sz, vp]
     L.srcnn_stage_merge_device.argtypes = [vp, u8p, u8p, u8p, C.c_int, C.c_int, sz, C.c_int, u8p, sz]
+    L.srcnn_fraw_scale_device.argtypes = [vp, vp, C.c_uint, C.c_uint, C.c_uint, C.c_uint, vp, C.c_int]
     _lib = L
     return L
 
@@ -266,6 +268,13 @@ class Engine:
         h, w = y.shape
         self._check(self.L.srcnn_stage_conv99x11_fp32_device(self.ctx, _dptr(y), w, h, y.stride(0), _dptr(act2)))
         return act2
+
+    def fraw_scale(self, src, dst, filter=2):
+        """frawscale-compatible resize of a float32 device plane (src/frawscale.cpp:162-286); filter 0/1/2 = box/bilinear/bicubic"""
+        sh, sw = src.shape
+        dh, dw = dst.shape
+        self._check(self.L.srcnn_fraw_scale_device(self.ctx, _dptr(src), sw, sh, dw, dh, _dptr(dst), int(filter)))
+        return dst
 
     def stage_merge(self, y, cr, cb, dst, order=ORDER_BGR):
         h, w = y.shape
