@@ -131,6 +131,7 @@ struct ResizeDev {
     const int* yofs;
     const short4* ycoef;
     int simd_w;
+    int quad_ok;   // every aligned group of 4 output columns spans <= 4 source columns (true for any up-scale)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -188,7 +189,7 @@ __device__ __forceinline__ uint32_t sat_u8_rn(float v) {
 }
 
 __global__ void __launch_bounds__(256) k_color_bicubic_tiled(ResizeDev p) {
-    __shared__ uint8_t sP[3][kMaxSR][kMaxSC];
+    __shared__ __align__(16) uint8_t sP[3][kMaxSR][kMaxSC + 8];   // +8: the 3-word window read of the last quad may run past a row
     // horizontal sums kept as float: they are integers below 2^24, so the conversion is exact and is done
     // once per sum instead of once per use in the vertical pass
     __shared__ __align__(16) float sH[3][kMaxSR][kTW];
@@ -201,9 +202,10 @@ __global__ void __launch_bounds__(256) k_color_bicubic_tiled(ResizeDev p) {
     const int nsc = sx_hi - sx_lo + 1, nsr = sy_hi - sy_lo + 1;
     const int tid = threadIdx.x;
 
-    // (1) colour-convert the footprint (replicate border applied here)
+    // (1) colour-convert the footprint (replicate border applied here); i / nsc by multiply-shift (exact for i < 2^12)
+    const unsigned rcp20 = ((1u << 20) + (unsigned)nsc - 1u) / (unsigned)nsc;
     for (int i = tid; i < nsr * nsc; i += 256) {
-        const int r = i / nsc, c = i - r * nsc;
+        const int r = (int)(((unsigned)i * rcp20) >> 20), c = i - r * nsc;
         const int gy = clampi(sy_lo + r, 0, p.sh - 1) - p.src_row0;
         const int gx = clampi(sx_lo + c, 0, p.sw - 1);
         const uint8_t* px = p.src + (size_t)gy * p.src_stride + 3 * (size_t)gx;
@@ -217,8 +219,44 @@ __global__ void __launch_bounds__(256) k_color_bicubic_tiled(ResizeDev p) {
     }
     __syncthreads();
 
-    // (2) integer horizontal pass: thread owns one output column, walks footprint rows
-    {
+    // (2) integer horizontal pass.  Fast form (any up-scale): a thread owns 4 adjacent output columns; their taps lie
+    //     in one 8-byte window of the converted row, fetched as three aligned words + funnel shifts, and each sum is
+    //     two dp2a (signed 16-bit taps x unsigned 8-bit pixels).  Slow form: one column per thread, byte loads.
+    if (p.quad_ok) {
+        const int q = tid & 15, col = q * 4, dx = dx0 + col;
+        if (dx < dx1) {
+            const int s0 = p.xofs[dx] - 1 - sx_lo;
+            int off[4];
+            uint32_t k01[4], k23[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int dxj = min(dx + j, dx1 - 1);           // columns past the tile edge repeat the last one (never stored)
+                off[j] = 8 * (p.xofs[dxj] - p.xofs[dx]);
+                const short4 cx = p.xcoef[dxj];
+                k01[j] = ((uint32_t)(unsigned short)cx.x) | ((uint32_t)(unsigned short)cx.y << 16);
+                k23[j] = ((uint32_t)(unsigned short)cx.z) | ((uint32_t)(unsigned short)cx.w << 16);
+            }
+            const int wsh = 8 * (s0 & 3);
+            for (int r = tid >> 4; r < nsr; r += 16) {
+#pragma unroll
+                for (int pl = 0; pl < 3; pl++) {
+                    const uint32_t* w = reinterpret_cast<const uint32_t*>(&sP[pl][r][s0 & ~3]);
+                    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+                    const uint32_t lo = __funnelshift_r(w0, w1, wsh), hi = __funnelshift_r(w1, w2, wsh);
+                    float h[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const uint32_t px4 = __funnelshift_rc(lo, hi, off[j]);
+                        int acc;
+                        asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(acc) : "r"(k01[j]), "r"(px4), "r"(0));
+                        asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(acc) : "r"(k23[j]), "r"(px4), "r"(acc));
+                        h[j] = (float)acc;
+                    }
+                    *reinterpret_cast<float4*>(&sH[pl][r][col]) = make_float4(h[0], h[1], h[2], h[3]);
+                }
+            }
+        }
+    } else {
         const int col = tid & (kTW - 1);
         const int dx = dx0 + col;
         if (dx < dx1) {
@@ -301,6 +339,9 @@ int launch_color_bicubic(Ctx* c, const ResizeArgs& a) {
         int dy1 = std::min(dy0 + kTH, a.row_end);
         if (a.ty->h_ofs[dy1 - 1] - a.ty->h_ofs[dy0] + 4 > kMaxSR) fits = false;
     }
+    p.quad_ok = 1;
+    for (int dx = 0; dx + 3 < a.ow && p.quad_ok; dx += 4)
+        if (a.tx->h_ofs[dx + 3] - a.tx->h_ofs[dx] > 4) p.quad_ok = 0;
     if (fits) {
         dim3 grid((a.ow + kTW - 1) / kTW, (rows + kTH - 1) / kTH);
         k_color_bicubic_tiled<<<grid, 256, 0, c->stream>>>(p);
