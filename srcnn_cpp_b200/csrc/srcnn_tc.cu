@@ -175,6 +175,11 @@ __device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a_tmem, uint64_t b, 
         "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc)
         : "memory");
 }
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.b32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+    return pred;
+}
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -285,7 +290,10 @@ __device__ __forceinline__ void taps_col(float (&acc)[8][5], const uint32_t* tv,
 __global__ void __launch_bounds__(kThreads, 1) k_srcnn_tc(const Params p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x;
-    const int warp = tid >> 5;
+    // warp index through a shuffle: provably warp-uniform, so ptxas keeps everything derived from it (roles, TMEM
+    // addresses, descriptors) in uniform registers and emits back-to-back UTCHMMA.  With a (tid & 31) == 0 branch it
+    // wraps EVERY tcgen05.mma in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop (~100 cycles per MMA).
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const bool issuer = warp >= 8;
     const int irole = issuer ? (warp - 8) % 6 : 0;        // 0,1: conv1 half a/b; 2..5: conv2+conv3 of column irole-2
     const int pipe = issuer ? (warp - 8) / 6 : (tid >> 7);
@@ -329,7 +337,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_srcnn_tc(const Params p) {
 
     if (issuer) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");   // the three issuer warpgroups hand registers to the epilogues
-        if ((tid & 31) == 0) {
+        const uint32_t leader = elect_one();   // the whole warp walks the loop (uniform control flow); one lane issues
+        {
             mbar_wait(wbar, 0, p.guard, 1);
             uint32_t ph = 0;   // every request barrier completes exactly once per group
             while (lin < lin_end) {
@@ -352,11 +361,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_srcnn_tc(const Params p) {
                         const int j = g >> 1, half = g & 1;
                         const uint32_t a0 = ring + (j & (kRingSlots - 1)) * kChunkBytes;
                         const uint32_t b0 = sbase + kOffW + half * 9 * kB1Tile + bofs;
-                        mma_ss(dcol, smem_desc(sbase + kOffOnes, 2048, 128), smem_desc(sbase + kOffBias1 + bofs, 4096, 128), idesc_f16(128), 0);
+                        if (leader) {
+                            mma_ss(dcol, smem_desc(sbase + kOffOnes, 2048, 128), smem_desc(sbase + kOffBias1 + bofs, 4096, 128), idesc_f16(128), 0);
 #pragma unroll
-                        for (int i = 0; i < 9; i++)
-                            mma_ss(dcol, smem_desc(a0 + i * 16, kChunkBytes, 128), smem_desc(b0 + i * kB1Tile, 4096, 128), idesc_f16(128), 1);
-                        mma_commit(MB(0, h));
+                            for (int i = 0; i < 9; i++)
+                                mma_ss(dcol, smem_desc(a0 + i * 16, kChunkBytes, 128), smem_desc(b0 + i * kB1Tile, 4096, 128), idesc_f16(128), 1);
+                            mma_commit(MB(0, h));
+                        }
+                        __syncwarp();
                     }
                 } else {
                     // ---- conv2 and conv3 of one output column d ----
@@ -366,19 +378,25 @@ __global__ void __launch_bounds__(kThreads, 1) k_srcnn_tc(const Params p) {
                         // conv2: D2[d] = b2 + A1[d] (TMEM) x W2, K = 64 in 4 steps
                         mbar_wait(RQ(1, h), ph, p.guard, 6);
                         tc_fence_after();
-                        mma_ss(hb + 64 + dl * 32, smem_desc(sbase + kOffOnes, 2048, 128), smem_desc(sbase + kOffBias2, 512, 128), idesc_f16(32), 0);
+                        if (leader) {
+                            mma_ss(hb + 64 + dl * 32, smem_desc(sbase + kOffOnes, 2048, 128), smem_desc(sbase + kOffBias2, 512, 128), idesc_f16(32), 0);
 #pragma unroll
-                        for (int ks = 0; ks < 4; ks++)
-                            mma_ts(hb + 64 + dl * 32, hb + dl * 32 + ks * 8, smem_desc(sbase + kImgB2 + ks * 1024, 512, 128), idesc_f16(32), 1);
-                        mma_commit(MB(1, h));
+                            for (int ks = 0; ks < 4; ks++)
+                                mma_ts(hb + 64 + dl * 32, hb + dl * 32 + ks * 8, smem_desc(sbase + kImgB2 + ks * 1024, 512, 128), idesc_f16(32), 1);
+                            mma_commit(MB(1, h));
+                        }
+                        __syncwarp();
                         // conv3 tap GEMM: T[d][tap] = A2[d] (TMEM) x W3, K = 32 in 2 steps
                         mbar_wait(RQ(2, h), ph, p.guard, 7);
                         ph ^= 1;
                         tc_fence_after();
+                        if (leader) {
 #pragma unroll
-                        for (int ks = 0; ks < 2; ks++)
-                            mma_ts(hb + dl * 32, hb + 64 + dl * 16 + ks * 8, smem_desc(sbase + kImgB3 + ks * 1024, 512, 128), idesc_f16(32), ks > 0);
-                        mma_commit(MB(2, h));
+                            for (int ks = 0; ks < 2; ks++)
+                                mma_ts(hb + dl * 32, hb + 64 + dl * 16 + ks * 8, smem_desc(sbase + kImgB3 + ks * 1024, 512, 128), idesc_f16(32), ks > 0);
+                            mma_commit(MB(2, h));
+                        }
+                        __syncwarp();
                     }
                 }
             }
