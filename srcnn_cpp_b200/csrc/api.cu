@@ -85,7 +85,7 @@ static int carve_planes(Ctx* c, int ow, int rows, int row0, Planes* pl) {
 
 static int run_cnn(Ctx* c, int variant, const CnnArgs& a) {
     if (variant == SRCNN_VARIANT_FP32) return launch_cnn_fp32(c, a, nullptr);
-    if (variant == SRCNN_VARIANT_TC) return launch_cnn_tc(c, a);
+    if (variant == SRCNN_VARIANT_TC) return c->tc_kernel == 1 ? launch_cnn_tc(c, a) : launch_cnn_tc2(c, a);
     return fail(c, SRCNN_E_ARG, "unknown variant %d", variant);
 }
 
@@ -209,6 +209,9 @@ int srcnn_create(srcnn_ctx** out, int device, int variant) {
     if (cudaHostGetDevicePointer((void**)&c->d_guard, c->h_guard, 0) != cudaSuccess) return bail(SRCNN_E_CUDA);
     int rc = tc_prepare_weights(c, (const float*)srcnn_weights_blob);
     if (rc) return bail(rc);
+    rc = tc2_prepare_weights(c, (const float*)srcnn_weights_blob);
+    if (rc) return bail(rc);
+    if (const char* k = getenv("SRCNN_TC_KERNEL")) c->tc_kernel = atoi(k) == 1 ? 1 : 2;
     *out = c;
     return SRCNN_OK;
 }
@@ -218,6 +221,7 @@ int srcnn_destroy(srcnn_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     tc_release(c);
+    tc2_release(c);
     for (auto& t : c->taps) {
         if (t.d_ofs) cudaFree(t.d_ofs);
         if (t.d_coef) cudaFree(t.d_coef);

@@ -69,6 +69,8 @@ struct Ctx {
     float* d_params = nullptr;       // the 8129 fp32 parameters (FP32 variant reads these)
     void* d_tc_weights = nullptr;    // packed FP16 operand images for the tcgen05 kernel
     size_t tc_weights_bytes = 0;
+    void* d_tc2_weights = nullptr;   // same for the row-walking kernel (srcnn_tc2.cu)
+    int tc_kernel = 2;               // 2 = row-walking kernel (default), 1 = first-generation kernel (SRCNN_TC_KERNEL=1)
     int* d_guard = nullptr;          // device-side watchdog flag (mapped pinned)
     int* h_guard = nullptr;
 
@@ -143,6 +145,9 @@ int launch_cnn_fp32(Ctx* c, const CnnArgs& a, float* act2_out /* optional full a
 int launch_cnn_tc(Ctx* c, const CnnArgs& a);
 int tc_prepare_weights(Ctx* c, const float* params);
 void tc_release(Ctx* c);
+int launch_cnn_tc2(Ctx* c, const CnnArgs& a);
+int tc2_prepare_weights(Ctx* c, const float* params);
+void tc2_release(Ctx* c);
 
 }  // namespace srcnn
 

@@ -1,0 +1,797 @@
+// srcnn_tc2.cu -- K-B-tc, second generation: the fused SRCNN kernel as a ROW-WALKING tcgen05 pipeline.
+//
+// Replaces Convolution99x11 (src/srcnn.cpp:254-325) and Convolution55 (src/srcnn.cpp:189-243) of the
+// reference with ONE persistent kernel; the 64- and 32-channel activations never leave the SM.
+// Operands are FP16 (Y is exact in FP16), accumulators FP32 in TMEM.
+//
+// Mapping (B200-first, not a translation of the CPU loops):
+//   * GEMM M dimension = 128 consecutive PIXELS OF ONE IMAGE ROW (one TMEM lane per pixel column).  A work
+//     item is a vertical strip of 124 output columns (lanes 2..125; +-2 lanes are conv3's horizontal reach)
+//     walked top to bottom, one image row per step.
+//   * conv1 is a dense im2col GEMM whose A operand lives in TENSOR MEMORY as a rolling ring: for every new image
+//     row each lane packs its 9 horizontal taps (Y[r][c-4..c+4], FP16) into a 5-column slot of a 10-slot ring
+//     (tcgen05.st); conv1 of output row r reads the nine slots of rows r-4..r+4 -- 7 x (M128 N64 K16) MMAs with
+//     A from TMEM, K = 112 (90 taps + bias + padding), against one of ten pre-rotated weight images (which slot
+//     holds which kernel row depends on r mod 10).  Each pixel's taps are written ONCE and reused by nine rows,
+//     so conv1 executes 14 336 FLOP/px instead of the 20 480 of a Toeplitz-weight GEMM off shared memory, and
+//     its A operand never touches the shared-memory port.
+//   * The bias of conv1 sits in the K padding (a constant-ones ring column times hi+lo FP16 bias rows); conv2
+//     borrows the same ones column for its bias MMA.  Epilogues are pure ReLU + FP16 pack.
+//   * conv2 = 4+1 x (M128 N32 K16) with A = packed activations written back to TMEM in place; conv3 = "tap
+//     GEMM" T[p][tap] = sum_c act2[p][c]*w3[c][tap] (2 x M128 N32 K16) followed by 25 shifted adds per pixel:
+//     vertical taps accumulate in registers while the strip is walked (sliding 5-row window), horizontal taps
+//     cross lanes through a small shared-memory exchange.
+//   * The reference's two border clamps are reproduced exactly: conv1 reads the replicate-clamped Y (applied
+//     when a row is staged), conv3 reads act2 AT THE CLAMPED PIXEL (src/srcnn.cpp:203,209) -- out-of-image taps
+//     fold onto the edge row of T, the horizontal exchange clamps its lane index; never by padding Y.
+//   * Warp specialisation by PHASE, not by tile: per strip pipeline one warpgroup does E1 (D1 -> ReLU/pack ->
+//     A1), one does E2 (D2 -> A2) plus the im2col ring producer, one does E3 (tap sums, exchange, store), and one
+//     elected lane of an issuer warp issues every MMA of the pipeline in order (with warp-uniform control flow a
+//     single thread issues tcgen05.mma at the tensor-pipe rate; tools/microbench/mma_rate5.cu).  Three rows
+//     ("units", 64 TMEM columns each) are in flight per pipeline, two pipelines per CTA share the tensor pipe.
+//
+// Executed tensor work per pixel: conv1 2*112*64 = 14 336, conv2 2*80*32 = 5 120, conv3 2*32*32 = 2 048 FLOP
+// (x 128/124 for the strip halo); algorithmic 16 064 FLOP/px is what bench.py reports against the roofline.
+#include <cuda_fp16.h>
+#include <cstdlib>
+#include <algorithm>
+#include <type_traits>
+
+#include "common.h"
+
+namespace srcnn {
+namespace tc2 {
+
+// ---------------------------------------------------------------------------------------------
+// geometry
+// ---------------------------------------------------------------------------------------------
+constexpr int kStripCols = 124;                   // valid output columns per strip = TMEM lanes 2..125
+constexpr int kSlots = 10;                        // im2col ring: 10 image rows x 5 TMEM columns (9 taps + pad)
+constexpr int kSlotCols = 5;
+constexpr int kC1Chunks = 7;                      // conv1 K = 112 = 7 x 16  (56 TMEM columns)
+constexpr int kOnesCol = 50;                      // ring column holding (1.0, 1.0): bias rows of conv1 / conv2
+constexpr int kUnits = 3;                         // rows in flight per pipeline
+constexpr int kUnitCols = 64;
+constexpr int kRingOff = kUnits * kUnitCols;      // ring columns [192, 248) of the pipeline's 256
+constexpr int kPipeCols = 256;
+
+constexpr int kB1Chunk = 64 * 16 * 2;             // one [N = 64][K = 16] tile
+constexpr int kB1Var = kC1Chunks * kB1Chunk;      // one rotation of the conv1 weights
+constexpr int kB1Bytes = kSlots * kB1Var;         // 143 360
+constexpr int kB2Bytes = 5 * 32 * 16 * 2;         // 4 K steps + bias step
+constexpr int kB3Bytes = 2 * 32 * 16 * 2;
+constexpr int kWeightBytes = kB1Bytes + kB2Bytes + kB3Bytes;   // 150 528
+constexpr int kYRowBytes = 288;                   // staged Y row: 2 pad + 136 px + 6 pad FP16
+constexpr int kYSlots = 4;
+constexpr int kHxBytes = 2 * 5 * 128 * 4;         // horizontal-tap exchange, double buffered: [buf][n][lane] fp32
+
+constexpr int kOffW = 0;
+constexpr int kImgB2 = kOffW + kB1Bytes;
+constexpr int kImgB3 = kImgB2 + kB2Bytes;
+constexpr int kOffY = kOffW + kWeightBytes;
+constexpr int kOffHx = kOffY + 2 * kYSlots * kYRowBytes;
+constexpr int kOffBar = kOffHx + 2 * kHxBytes;
+constexpr int kBarsPerPipe = 35;                  // D1full[3] D2full[3] Tfull[3] | A1ready[3] A2ready[3] unitfree[3] | ringready[16] | hx
+constexpr int kOffTmem = kOffBar + 8 + 2 * kBarsPerPipe * 8;
+constexpr int kSmemBytes = kOffTmem + 64;
+constexpr int kThreads = 896;                     // 2 x (E1, E2+producer, E3) warpgroups + one issuer warpgroup
+static_assert(kWeightBytes % 64 == 0 && kSmemBytes <= 227 * 1024, "shared memory budget");
+
+__constant__ float c_b3;
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+__device__ __forceinline__ uint32_t mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(hint_ns)
+        : "memory");
+    return ok;
+}
+// bounded wait: a protocol bug must surface as an error code, never as a hung GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* guard, int code) {
+    if (mbar_try_wait(bar, parity)) return;
+    uint32_t tries = 0;
+    while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+        if (++tries > 100000u) {   // >> any legitimate wait (each try parks for up to 20 us)
+            *guard = code;
+            __threadfence_system();
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.b32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+    return pred;
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// shared-memory matrix descriptor, SWIZZLE_NONE, K-major canonical layout: 8 rows x 16 B core matrices,
+// LBO = byte distance between the two K halves of a K=16 step, SBO = byte distance between 8-row groups
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+           (1ull << 46);
+}
+// instruction descriptor: kind::f16, A=B=FP16, D=FP32, both K-major, M=128
+__host__ __device__ constexpr uint32_t idesc_f16(int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d),
+        "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+#define TM_R(v, o) "=r"(v[o + 0]), "=r"(v[o + 1]), "=r"(v[o + 2]), "=r"(v[o + 3]), "=r"(v[o + 4]), "=r"(v[o + 5]), "=r"(v[o + 6]), "=r"(v[o + 7])
+#define TM_W(v, o) "r"(v[o + 0]), "r"(v[o + 1]), "r"(v[o + 2]), "r"(v[o + 3]), "r"(v[o + 4]), "r"(v[o + 5]), "r"(v[o + 6]), "r"(v[o + 7])
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : TM_R(v, 0), TM_R(v, 8), TM_R(v, 16), TM_R(v, 24)
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : TM_R(v, 0), TM_R(v, 8)
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : TM_R(v, 0) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t& v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+        "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+        TM_W(v, 0), TM_W(v, 8), TM_W(v, 16), TM_W(v, 24)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+        TM_W(v, 0), TM_W(v, 8)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), TM_W(v, 0) : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void tmem_st1(uint32_t taddr, uint32_t a) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(a) : "memory");
+}
+// ReLU + round-to-nearest FP16 + pack: low half = first element (even K index)
+__device__ __forceinline__ uint32_t relu_pack_f16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel parameters
+// ---------------------------------------------------------------------------------------------
+struct Params {
+    const uint8_t* y;      // plane row 0 = image row `row0`; rows [row0, row0+rows) are present
+    size_t pitch;
+    int W, H;
+    int row0, rows;
+    int out_begin, out_end;  // image rows to produce
+    uint8_t* out;          // same row0 convention as y
+    size_t out_pitch;
+    const uint8_t* wimg;   // packed FP16 operand image (kWeightBytes)
+    long long total;       // strips x (out_end - out_begin) row steps
+    int* guard;
+    long long* dbg;        // optional timeline (SRCNN_TC_DEBUG=1): clock64 stamps of pipeline 0 of CTA 0, first segment
+};
+constexpr int kDbgRows = 64, kDbgSlots = 8;
+#define TL2(role_, row_, slot_)                                                                                   \
+    do {                                                                                                          \
+        if constexpr (DBG)                                                                                        \
+            if (blockIdx.x == 0 && pipe == 0 && (ROLE >= 3 ? (threadIdx.x & 31) == 0 : tp == 0) && first_seg &&  \
+                (row_) >= 0 && (row_) < kDbgRows)                                                                 \
+                p.dbg[(((role_) * kDbgRows) + (row_)) * kDbgSlots + (slot_)] = clock64();                        \
+    } while (0)
+
+// a (unit, phase parity) cursor over the three units of a pipeline: one step per image row, forever
+struct UnitCursor {
+    uint32_t u = 0, par = 0;
+    __device__ __forceinline__ void next() {
+        if (++u == (uint32_t)kUnits) { u = 0; par ^= 1u; }
+    }
+};
+// same for the sixteen ring-row barriers
+struct RingCursor {
+    uint32_t idx = 0, par = 0;
+    __device__ __forceinline__ void next() {
+        idx = (idx + 1u) & 15u;
+        if (idx == 0u) par ^= 1u;
+    }
+    __device__ __forceinline__ void advance(uint32_t n) {
+        const uint32_t q = idx + n;
+        idx = q & 15u;
+        par ^= (q >> 4) & 1u;
+    }
+};
+
+// ---- E3 helpers (free functions with explicit state: the five phases of the row ring inline without spills) ----
+struct E3Ctx {
+    const Params& p;
+    float* hx;
+    uint32_t hxbar, bars, tml;
+    int x, tp, pipe, ta, tb, ra, rb;
+    bool col_ok, first_seg;
+};
+// store the row that was published to the horizontal exchange one step ago
+__device__ __forceinline__ void e3_emit(const E3Ctx& c, const int (&ln)[5], const uint32_t npub, int& pend_r) {
+    const uint32_t k = npub - 1u;
+    mbar_wait(c.hxbar, k & 1u, c.p.guard, 41);         // all 128 lanes have published row pend_r
+    const float* hb = c.hx + (k & 1u) * (5 * 128);
+    float sum = hb[0 * 128 + ln[0]];
+#pragma unroll
+    for (int n = 1; n < 5; n++) sum += hb[n * 128 + ln[n]];
+    sum += c_b3;                                // src/srcnn.cpp:235
+    int q = (int)sum;                           // :238 truncation toward zero
+    q = min(max(q, 0), 255);
+    if (c.col_ok) c.p.out[(size_t)(pend_r - c.p.row0) * c.p.out_pitch + c.x] = (uint8_t)q;
+    pend_r = -1;
+}
+// one T row: acc[k] = pending output row rho-2+k (the window slides down one row per step)
+template <bool DBG>
+__device__ __forceinline__ void e3_step(const E3Ctx& c, const int (&ln)[5], float (&acc)[5][5], const int rho, UnitCursor& uc, uint32_t& npub, int& pend_r) {
+    constexpr int ROLE = 2;
+    const Params& p = c.p;
+    const int pipe = c.pipe, tp = c.tp;
+    const bool first_seg = c.first_seg;
+    (void)p; (void)pipe; (void)tp; (void)first_seg; (void)ROLE;
+    const bool has_t = rho <= c.tb;
+    uint32_t tv[25];   // the 25 taps: three loads (16 + 8 + 1 columns) instead of one 32-register block
+    TL2(2, rho - c.ta, 0);
+    if (has_t) {
+        mbar_wait(c.bars + (6 + uc.u) * 8, uc.par, p.guard, 40);   // TFULL
+        tc_fence_after();
+        tmem_ld16(c.tml + uc.u * kUnitCols, tv);     // in flight while the previous row is stored
+        tmem_ld8(c.tml + uc.u * kUnitCols + 16, tv + 16);
+        tmem_ld1(c.tml + uc.u * kUnitCols + 24, tv[24]);
+    }
+    TL2(2, rho - c.ta, 1);
+    if (pend_r >= 0) e3_emit(c, ln, npub, pend_r);
+    TL2(2, rho - c.ta, 2);
+    if (has_t) {
+        tc_wait_ld();
+        tc_fence_before();
+        mbar_arrive(c.bars + (15 + uc.u) * 8);       // UNITFREE
+        uc.next();
+        // T[m*5+n] belongs to output row rho - (m-2): window position k = 4 - m
+#pragma unroll
+        for (int m = 0; m < 5; m++)
+#pragma unroll
+            for (int n = 0; n < 5; n++) acc[4 - m][n] += __uint_as_float(tv[m * 5 + n]);
+        if (rho == 0) {        // rows -1, -2 clamp onto row 0 (src/srcnn.cpp:203)
+#pragma unroll
+            for (int n = 0; n < 5; n++) {
+                acc[2][n] += __uint_as_float(tv[0 * 5 + n]) + __uint_as_float(tv[1 * 5 + n]);
+                acc[3][n] += __uint_as_float(tv[0 * 5 + n]);
+            }
+        }
+        if (rho == p.H - 1) {    // rows H, H+1 clamp onto row H-1
+#pragma unroll
+            for (int n = 0; n < 5; n++) {
+                acc[2][n] += __uint_as_float(tv[3 * 5 + n]) + __uint_as_float(tv[4 * 5 + n]);
+                acc[1][n] += __uint_as_float(tv[4 * 5 + n]);
+            }
+        }
+    }
+    TL2(2, rho - c.ta, 3);
+    const int r = rho - 2;
+    if (r >= c.ra && r < c.rb) {       // output row r is complete: publish its five horizontal-tap partial sums
+        float* hb = c.hx + (npub & 1u) * (5 * 128);
+#pragma unroll
+        for (int n = 0; n < 5; n++) hb[n * 128 + tp] = acc[0][n];
+        mbar_arrive(c.hxbar);
+        npub++;
+        pend_r = r;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+#pragma unroll
+        for (int n = 0; n < 5; n++) acc[k][n] = acc[k + 1][n];
+#pragma unroll
+    for (int n = 0; n < 5; n++) acc[4][n] = 0.f;
+    TL2(2, rho - c.ta, 4);
+}
+
+// One role's whole life: the segment loop of a pipeline.  Each role sits in its own branch of the kernel so that its
+// setmaxnreg governs the register allocation of exactly its code.
+//   ROLE 0: E1 + E2   1: im2col ring producer   2: E3   3: conv1 issuer   4: conv2 + conv3 issuer
+template <int ROLE, bool DBG>
+__device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const uint32_t sbase, const uint32_t wbar, const uint32_t bars,
+                                          const uint32_t tm, const uint32_t tml, const uint32_t ring, const int pipe, const int tp) {
+    auto D1FULL = [&](uint32_t u) { return bars + (0 + u) * 8; };
+    auto D2FULL = [&](uint32_t u) { return bars + (3 + u) * 8; };
+    auto TFULL = [&](uint32_t u) { return bars + (6 + u) * 8; };
+    auto A1READY = [&](uint32_t u) { return bars + (9 + u) * 8; };
+    auto A2READY = [&](uint32_t u) { return bars + (12 + u) * 8; };
+    auto UNITFREE = [&](uint32_t u) { return bars + (15 + u) * 8; };
+    auto RINGREADY = [&](uint32_t idx) { return bars + (18 + idx) * 8; };
+    const uint32_t HXBAR = bars + 34 * 8;
+    const int W = p.W, H = p.H;
+    const int Hb = p.out_end - p.out_begin;
+    const long long nworkers = (long long)gridDim.x * 2;
+    const long long wk = (long long)blockIdx.x * 2 + pipe;
+    long long lin = p.total * wk / nworkers;
+    const long long lin_end = p.total * (wk + 1) / nworkers;
+    const int segbar = 8 + pipe;     // named barrier that closes a segment (3 warpgroups + the two issuer warps)
+    bool first_seg = true;
+    (void)first_seg;
+
+    // barrier cursors run on across segments (every row / ring row arrives exactly once on its barrier)
+    UnitCursor uc, uc2;              // uc: this role's main row cursor; uc2: second stage of the role (E2 / conv3 / ring-free)
+    RingCursor rc;                   // producer: ring row being written; conv1 issuer: ring row being waited for
+    uint32_t rows_done = 0;          // conv1 issuer: rows issued so far (the first three find their unit free)
+    uint32_t npub = 0;               // E3: rows published to the horizontal exchange so far
+    (void)rows_done; (void)npub;
+
+    if constexpr (ROLE == 1) {   // the ring starts as finite zeros (stale TMEM bits could be NaN: 0 x NaN = NaN) + the ones column
+        uint32_t z[32];
+#pragma unroll
+        for (int i = 0; i < 32; i++) z[i] = 0u;
+        tmem_st32(tml + kRingOff, z);
+        tmem_st16(tml + kRingOff + 32, z);
+        tmem_st8(tml + kRingOff + 48, z);
+        tc_wait_st();
+        tmem_st1(tml + kRingOff + kOnesCol, 0x3C003C00u);
+        tc_wait_st();
+    }
+    if constexpr (ROLE >= 3) mbar_wait(wbar, 0, p.guard, 1);   // packed operands have landed in shared memory
+
+    while (lin < lin_end) {
+        // ---- one segment: strip `strip`, output rows [ra, rb) ----
+        const int strip = (int)(lin / Hb);
+        const int rfirst = (int)(lin - (long long)strip * Hb);
+        const int cnt = (int)min((long long)(Hb - rfirst), lin_end - lin);
+        lin += cnt;
+        const int xs = strip * kStripCols;
+        const int ra = p.out_begin + rfirst, rb = ra + cnt;
+        const int ta = max(ra - 2, 0), tb = min(rb + 1, H - 1);   // act2 / T rows of the segment (image rows)
+        const int nT = tb - ta + 1;                               // >= 1
+        const int nP = nT + 8;                                    // ring rows: virtual image rows ta-4 .. tb+4
+        // ring slot by ABSOLUTE image row (virtual row v -> slot (v + 10) mod 10): a row's conv1 always sees the same K
+        // order, so results do not depend on how the image was cut into segments or bands
+        const uint32_t slot0 = (uint32_t)((ta + 6) % kSlots);
+
+        if constexpr (ROLE == 3) {
+            // ================= conv1 issuer (one elected lane): D1[u] = ring x W1[rotation] =================
+            const uint32_t leader = elect_one();
+            uint32_t rot = slot0;                 // rotation = slot of the window's first ring row
+            rc.advance(8);                        // conv1 of row i needs ring rows i .. i+8: wait for the last one
+            for (int i = 0; i < nT; i++) {
+                TL2(3, i, 0);
+                // sixteen barriers: the issuer skips the first eight ring rows of a segment, and a parity wait is only sound
+                // when every earlier phase of ITS barrier is already complete (rows q-16, q-32, ... are)
+                mbar_wait(RINGREADY(rc.idx), rc.par, p.guard, 10);
+                TL2(3, i, 1);
+                if (rows_done >= 3u) mbar_wait(UNITFREE(uc.u), uc.par ^ 1u, p.guard, 11);   // E3 has read T of row g-3
+                tc_fence_after();
+                TL2(3, i, 2);
+                if (leader) {
+                    const uint32_t d = tm + uc.u * kUnitCols;
+                    const uint32_t b = sbase + kOffW + rot * kB1Var;
+#pragma unroll
+                    for (int ch = 0; ch < kC1Chunks; ch++)
+                        mma_ts(d, ring + ch * 8, smem_desc(b + ch * kB1Chunk, 1024, 128), idesc_f16(64), ch > 0);
+                    mma_commit(D1FULL(uc.u));
+                }
+                __syncwarp();
+                TL2(3, i, 3);
+                uc.next();
+                rc.next();
+                rows_done++;
+                if (++rot == (uint32_t)kSlots) rot = 0;
+            }
+        } else if constexpr (ROLE == 4) {
+            // ================= conv2 / conv3 issuer: conv2(i), conv3(i-1), in order =================
+            const uint32_t leader = elect_one();
+            for (int i = 0; i < nT + 1; i++) {
+                if (i < nT) {
+                    mbar_wait(A1READY(uc.u), uc.par, p.guard, 12);
+                    tc_fence_after();
+                    TL2(3, i, 4);
+                    if (leader) {
+                        const uint32_t un = tm + uc.u * kUnitCols;
+#pragma unroll
+                        for (int ks = 0; ks < 4; ks++)
+                            mma_ts(un + 32, un + ks * 8, smem_desc(sbase + kImgB2 + ks * 1024, 512, 128), idesc_f16(32), ks > 0);
+                        mma_ts(un + 32, ring + 48, smem_desc(sbase + kImgB2 + 4 * 1024, 512, 128), idesc_f16(32), 1);   // + b2
+                        mma_commit(D2FULL(uc.u));
+                    }
+                    __syncwarp();
+                    uc.next();
+                }
+                if (i >= 1) {
+                    mbar_wait(A2READY(uc2.u), uc2.par, p.guard, 13);
+                    tc_fence_after();
+                    TL2(3, i - 1, 5);
+                    if (leader) {
+                        const uint32_t un = tm + uc2.u * kUnitCols;
+#pragma unroll
+                        for (int ks = 0; ks < 2; ks++)
+                            mma_ts(un, un + 32 + ks * 8, smem_desc(sbase + kImgB3 + ks * 1024, 512, 128), idesc_f16(32), ks > 0);
+                        mma_commit(TFULL(uc2.u));
+                    }
+                    __syncwarp();
+                    uc2.next();
+                }
+            }
+        } else if constexpr (ROLE == 0) {
+            // ================= E1(i): D1 (64 ch fp32) -> ReLU, FP16 -> A1 (32 columns, in place) ==================
+            // ================= E2(i-1): D2 (32 ch fp32 at [32,64)) -> A2 (16 columns at [32,48), in place) ========
+            // merged so that E2's TMEM load flies while E1's stores drain
+            for (int i = 0; i < nT + 1; i++) {
+                const bool e1 = i < nT, e2 = i >= 1;
+                const uint32_t un1 = tml + uc.u * kUnitCols, un2 = tml + uc2.u * kUnitCols;
+                uint32_t va[32], vb[32];
+                TL2(0, i, 0);
+                if (e1) {
+                    mbar_wait(D1FULL(uc.u), uc.par, p.guard, 20);
+                    tc_fence_after();
+                    TL2(0, i, 1);
+                    tmem_ld32(un1, va);
+                    tmem_ld32(un1 + 32, vb);
+                }
+                if (e2) {
+                    mbar_wait(D2FULL(uc2.u), uc2.par, p.guard, 21);
+                    tc_fence_after();
+                }
+                TL2(0, i, 2);
+                if (e1) {
+                    tc_wait_ld();
+#pragma unroll
+                    for (int c = 0; c < 16; c++) va[c] = relu_pack_f16x2(__uint_as_float(va[2 * c]), __uint_as_float(va[2 * c + 1]));
+#pragma unroll
+                    for (int c = 0; c < 16; c++) vb[c] = relu_pack_f16x2(__uint_as_float(vb[2 * c]), __uint_as_float(vb[2 * c + 1]));
+                    tmem_st16(un1, va);
+                    tmem_st16(un1 + 16, vb);
+                }
+                TL2(0, i, 3);
+                if (e2) tmem_ld32(un2 + 32, va);
+                if (e1) {
+                    tc_wait_st();
+                    tc_fence_before();
+                    mbar_arrive(A1READY(uc.u));
+                    uc.next();
+                }
+                TL2(0, i, 4);
+                if (e2) {
+                    tc_wait_ld();
+#pragma unroll
+                    for (int c = 0; c < 16; c++) va[c] = relu_pack_f16x2(__uint_as_float(va[2 * c]), __uint_as_float(va[2 * c + 1]));
+                    tmem_st16(un2 + 32, va);
+                    tc_wait_st();
+                    tc_fence_before();
+                    mbar_arrive(A2READY(uc2.u));
+                    uc2.next();
+                }
+                TL2(0, i, 5);
+            }
+        } else if constexpr (ROLE == 1) {
+            // ================= im2col ring producer =================
+            const int ybar = 1 + pipe;
+            uint8_t* yst = smem + kOffY + pipe * (kYSlots * kYRowBytes);
+            const uint32_t yst_s = sbase + kOffY + pipe * (kYSlots * kYRowBytes);
+            const int xc0 = min(max(xs - 6 + tp, 0), W - 1);                 // tile column tp
+            const int xc1 = min(max(xs - 6 + 128 + (tp & 7), 0), W - 1);     // tile column 128 + (tp & 7)
+            auto fetch = [&](int q, uint32_t& v0, uint32_t& v1) {   // Y of ring row q at this thread's tile columns
+                int r = min(max(ta - 4 + q, 0), H - 1);
+                r = min(max(r - p.row0, 0), p.rows - 1);
+                const uint8_t* yrow = p.y + (size_t)r * p.pitch;
+                v0 = yrow[xc0];
+                if (tp < 8) v1 = yrow[xc1];   // no arithmetic on the loaded values here: nothing waits for the loads
+            };
+            auto stage = [&](int q, uint32_t v0, uint32_t v1) {   // exact u8 -> FP16 (integers below 2048 are exact)
+                uint8_t* row = yst + (q & (kYSlots - 1)) * kYRowBytes;
+                *reinterpret_cast<__half*>(row + 4 + tp * 2) = __ushort2half_rn((unsigned short)v0);
+                if (tp < 8) *reinterpret_cast<__half*>(row + 4 + (128 + tp) * 2) = __ushort2half_rn((unsigned short)v1);
+            };
+            uint32_t slot = slot0;
+            uc2 = uc;                              // ring-free cursor: conv1 of the segment's row t-10
+            // one ring row: gather 9 taps from the staged row, write the slot, stage row t+1, start loading row t+2
+            // (two register sets alternate so that a loaded value is first touched one full iteration later)
+            auto step = [&](int t, uint32_t& cur0, uint32_t& cur1, uint32_t& nxt0, uint32_t& nxt1) {
+                TL2(1, t, 0);
+                if (t + 2 < nP) fetch(t + 2, cur0, cur1);   // cur* held row t (already staged): free for row t+2
+                named_bar(ybar, 128);   // ring row t is staged
+                // 9 taps of lane tp = tile columns tp .. tp+8 = FP16 index 2 + tp .. of the staged row
+                const uint32_t rowaddr = yst_s + (t & (kYSlots - 1)) * kYRowBytes + 4 + ((tp >> 1) << 2);
+                uint32_t w[6], o[5];
+#pragma unroll
+                for (int k = 0; k < 6; k++) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w[k]) : "r"(rowaddr + 4 * k));
+                const uint32_t sh = (tp & 1) * 16;
+#pragma unroll
+                for (int k = 0; k < 5; k++) o[k] = __funnelshift_r(w[k], w[k + 1], sh);
+                o[4] &= 0xFFFFu;
+                TL2(1, t, 1);
+                if (t >= kSlots) {      // the slot's previous row was last read by conv1 of row t-10
+                    mbar_wait(D1FULL(uc2.u), uc2.par, p.guard, 30);
+                    tc_fence_after();
+                    uc2.next();
+                }
+                TL2(1, t, 2);
+                const uint32_t sl = tml + kRingOff + slot * kSlotCols;
+                tmem_st4(sl, o[0], o[1], o[2], o[3]);
+                tmem_st1(sl + 4, o[4]);
+                if (t + 1 < nP) stage(t + 1, nxt0, nxt1);
+                TL2(1, t, 3);
+                tc_wait_st();
+                tc_fence_before();
+                mbar_arrive(RINGREADY(rc.idx));
+                rc.next();
+                if (++slot == (uint32_t)kSlots) slot = 0;
+                TL2(1, t, 4);
+            };
+            uint32_t a0 = 0, a1 = 0, b0 = 0, b1 = 0;
+            fetch(0, a0, a1);
+            if (nP > 1) fetch(1, b0, b1);
+            stage(0, a0, a1);
+            for (int t = 0; t < nP; t += 2) {
+                step(t, a0, a1, b0, b1);
+                if (t + 1 < nP) step(t + 1, b0, b1, a0, a1);
+            }
+            for (int i = 0; i < nT; i++) uc.next();   // this role's row cursor only marks the segment start
+        } else {
+            // ================= E3: conv3 tap sums =================
+            float* hx = (float*)(smem + kOffHx + pipe * kHxBytes);
+            const int x = xs - 2 + tp;                         // image column of this lane
+            int ln[5];                                         // lanes holding act2 at clamp(x + n - 2)  (src/srcnn.cpp:209)
+#pragma unroll
+            for (int n = 0; n < 5; n++) ln[n] = min(max(min(max(x + n - 2, 0), W - 1) - (xs - 2), 0), 127);
+            const bool col_ok = (tp >= 2) && (tp <= 125) && (x < W);
+            float acc[5][5];                                   // ring of pending output rows x horizontal tap n
+#pragma unroll
+            for (int k = 0; k < 5; k++)
+#pragma unroll
+                for (int n = 0; n < 5; n++) acc[k][n] = 0.f;
+            int pend_r = -1;                                   // row published to the exchange, not yet stored
+            E3Ctx cx{p, hx, HXBAR, bars, tml, x, tp, pipe, ta, tb, ra, rb, col_ok, first_seg};
+            const int last = rb + 1;
+            for (int rho = ta; rho <= last; rho++) e3_step<DBG>(cx, ln, acc, rho, uc, npub, pend_r);
+            if (pend_r >= 0) e3_emit(cx, ln, npub, pend_r);
+        }
+        first_seg = false;
+        named_bar(segbar, 3 * 128 + 64);   // segment drained: every MMA waited for, ring and units reusable from scratch
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the kernel: 28 warps.
+//   warpgroups 0,1 : E1 + E2 of pipeline 0,1   (D1 -> ReLU + FP16 pack -> A1, D2 -> A2; one thread per TMEM lane)
+//   warpgroups 2,3 : im2col ring producer of pipeline 0,1
+//   warpgroups 4,5 : E3 of pipeline 0,1        (tap sums, horizontal exchange, bias, truncate, clamp, store)
+//   warpgroup  6   : warp 24 / 25 = conv1 issuer of pipeline 0 / 1, warp 26 / 27 = conv2+conv3 issuer of pipeline 0 / 1
+//                    (one elected lane each)
+// ---------------------------------------------------------------------------------------------
+template <bool DBG>
+__global__ void __launch_bounds__(kThreads, 1) k_srcnn_tc2(const Params p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform (see srcnn_tc.cu)
+    const int wg = warp >> 2;
+    const int role = wg < 6 ? (wg >> 1) : 3;                  // 0 E1+E2, 1 producer, 2 E3, 3 issuers
+    const int pipe = wg < 6 ? (wg & 1) : (warp & 1);
+    const int tp = tid & 127;                                  // TMEM lane = pixel column xs - 2 + tp
+    const int quarter = warp & 3;
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t wbar = sbase + kOffBar;
+    const uint32_t bars = sbase + kOffBar + 8 + pipe * (kBarsPerPipe * 8);
+    volatile uint32_t* tmem_slot = (volatile uint32_t*)(smem + kOffTmem);
+
+    if (tid == 0) {
+        mbar_init(wbar, 1);
+        for (int q = 0; q < 2; q++)
+            for (int i = 0; i < kBarsPerPipe; i++)
+                mbar_init(sbase + kOffBar + 8 + (q * kBarsPerPipe + i) * 8, i < 9 ? 1 : 128);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(smem_u32((const void*)tmem_slot), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tid == 0) {  // weights: one TMA bulk fetch per CTA, shared by both pipelines
+        mbar_expect_tx(wbar, kWeightBytes);
+        constexpr int kPiece = kWeightBytes / 4;
+        static_assert(kPiece % 16 == 0, "bulk copy granularity");
+        for (int i = 0; i < 4; i++) bulk_g2s(sbase + kOffW + i * kPiece, p.wimg + i * kPiece, kPiece, wbar);
+    }
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tm = tmem_base + pipe * kPipeCols;                   // this pipeline's columns
+    const uint32_t tml = tm + ((uint32_t)(quarter * 32) << 16);         // + this warp's lane quarter
+    const uint32_t ring = tm + kRingOff;
+
+    // register budget (64 512 at launch = 896 x 72): issuers 24, producer 56, E1+E2 96, E3 88
+    if (role == 3) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+        if (warp < 26) role_loop<3, DBG>(p, smem, sbase, wbar, bars, tm, tml, ring, pipe, tp);
+        else role_loop<4, DBG>(p, smem, sbase, wbar, bars, tm, tml, ring, pipe, tp);
+    } else if (role == 1) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        role_loop<1, DBG>(p, smem, sbase, wbar, bars, tm, tml, ring, pipe, tp);
+    } else if (role == 0) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
+        role_loop<0, DBG>(p, smem, sbase, wbar, bars, tm, tml, ring, pipe, tp);
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
+        role_loop<2, DBG>(p, smem, sbase, wbar, bars, tm, tml, ring, pipe, tp);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace tc2
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static inline void put_h2(uint8_t* img, size_t byte_off, float v) {
+    const __half h = __float2half_rn(v);
+    memcpy(img + byte_off, &h, 2);
+}
+
+// Packs the FP32 parameters into the FP16 operand images the kernel's UMMA descriptors expect
+// (SWIZZLE_NONE, K-major: element (n,k) of a [N][16] tile at (k/8)*(N*16) + n*16 + (k%8)*2 bytes).
+int tc2_prepare_weights(Ctx* c, const float* P) {
+    using namespace tc2;
+    std::vector<uint8_t> img(kWeightBytes, 0);
+    const float* w1 = P + kOffW1;
+    const float* w2 = P + kOffW2;
+    const float* w3 = P + kOffW3;
+    auto hi_lo = [](float b, float& hi, float& lo) {
+        hi = __half2float(__float2half_rn(b));
+        lo = b - hi;
+    };
+    // conv1, ten rotations: for output row i (segment-local) the ring slot s holds image row i-4+j with
+    // j = (s - i mod 10) mod 10 (j = 9: a row outside the 9x9 window -> zero weights).  K index k = 10*s + tap
+    // (tap 9 = the slot's padding half), k = 100/101 = the ones column -> hi/lo halves of the bias.
+    for (int v = 0; v < kSlots; v++)
+        for (int n = 0; n < 64; n++) {
+            for (int k = 0; k < 16 * kC1Chunks; k++) {
+                float val = 0.f;
+                if (k < 100) {
+                    const int s = k / 10, tap = k % 10;
+                    const int j = (s - v + kSlots) % kSlots;
+                    if (j <= 8 && tap <= 8) val = w1[(n * 9 + j) * 9 + tap];
+                } else if (k == 2 * kOnesCol || k == 2 * kOnesCol + 1) {
+                    float hi, lo;
+                    hi_lo(P[kOffB1 + n], hi, lo);
+                    val = (k == 2 * kOnesCol) ? hi : lo;
+                }
+                const int ch = k / 16, kk = k % 16;
+                put_h2(img.data(), (size_t)v * kB1Var + (size_t)ch * kB1Chunk + (size_t)(kk / 8) * 1024 + (size_t)n * 16 + (kk % 8) * 2, val);
+            }
+        }
+    for (int ks = 0; ks < 4; ks++)  // conv2: B[n = out ch][k = in ch ks*16+k]
+        for (int n = 0; n < 32; n++)
+            for (int k = 0; k < 16; k++)
+                put_h2(img.data(), kImgB2 + (size_t)ks * 1024 + (size_t)(k / 8) * 512 + (size_t)n * 16 + (k % 8) * 2,
+                       w2[n * 64 + ks * 16 + k]);
+    for (int n = 0; n < 32; n++) {  // conv2 bias step: A = ring columns 48..55, the ones column is K index 4,5 of it
+        float hi, lo;
+        hi_lo(P[kOffB2 + n], hi, lo);
+        const int k0 = 2 * (kOnesCol - 48);
+        put_h2(img.data(), kImgB2 + 4 * 1024 + (size_t)(k0 / 8) * 512 + (size_t)n * 16 + (k0 % 8) * 2, hi);
+        put_h2(img.data(), kImgB2 + 4 * 1024 + (size_t)((k0 + 1) / 8) * 512 + (size_t)n * 16 + ((k0 + 1) % 8) * 2, lo);
+    }
+    for (int ks = 0; ks < 2; ks++)  // conv3 tap GEMM: B[n = tap m*5+n][k = in ch]
+        for (int n = 0; n < 32; n++)
+            for (int k = 0; k < 16; k++)
+                put_h2(img.data(), kImgB3 + (size_t)ks * 1024 + (size_t)(k / 8) * 512 + (size_t)n * 16 + (k % 8) * 2,
+                       n < 25 ? w3[(ks * 16 + k) * 25 + n] : 0.f);
+    SRCNN_CUDA(c, cudaMalloc(&c->d_tc2_weights, kWeightBytes));
+    SRCNN_CUDA(c, cudaMemcpy(c->d_tc2_weights, img.data(), kWeightBytes, cudaMemcpyHostToDevice));
+    SRCNN_CUDA(c, cudaMemcpyToSymbol(tc2::c_b3, P + kOffB3, sizeof(float)));
+    SRCNN_CUDA(c, cudaFuncSetAttribute(tc2::k_srcnn_tc2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    SRCNN_CUDA(c, cudaFuncSetAttribute(tc2::k_srcnn_tc2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    return SRCNN_OK;
+}
+
+void tc2_release(Ctx* c) {
+    if (c->d_tc2_weights) cudaFree(c->d_tc2_weights);
+    c->d_tc2_weights = nullptr;
+}
+
+int launch_cnn_tc2(Ctx* c, const CnnArgs& a) {
+    using namespace tc2;
+    if (a.out_end <= a.out_begin) return SRCNN_OK;
+    Params p;
+    p.y = a.y; p.pitch = a.pitch;
+    p.W = a.W; p.H = a.H;
+    p.row0 = a.row0; p.rows = a.rows;
+    p.out_begin = a.out_begin; p.out_end = a.out_end;
+    p.out = a.out; p.out_pitch = a.out_pitch;
+    p.wimg = (const uint8_t*)c->d_tc2_weights;
+    const int nstrips = (a.W + kStripCols - 1) / kStripCols;
+    p.total = (long long)nstrips * (a.out_end - a.out_begin);
+    p.guard = c->d_guard;
+    p.dbg = nullptr;
+    if (getenv("SRCNN_TC_DEBUG")) {
+        const size_t bytes = 4 * kDbgRows * kDbgSlots * sizeof(long long);
+        int rc = ensure(c, c->work_buf, bytes);
+        if (rc) return rc;
+        cudaMemsetAsync(c->work_buf.p, 0, bytes, c->stream);
+        p.dbg = (long long*)c->work_buf.p;
+    }
+    // one persistent CTA per SM; fewer when the image is too small to give every pipeline ~48 row steps
+    long long want = (p.total + 95) / 96;
+    int grid = (int)std::min<long long>(c->sm_count, std::max<long long>(1, want));
+    if (p.dbg) k_srcnn_tc2<true><<<grid, kThreads, kSmemBytes, c->stream>>>(p);
+    else k_srcnn_tc2<false><<<grid, kThreads, kSmemBytes, c->stream>>>(p);
+    c->launches++;
+    SRCNN_CUDA(c, cudaGetLastError());
+    return SRCNN_OK;
+}
+
+}  // namespace srcnn
+
+// debug hook: copies the last launch's timeline (4 roles x 64 rows x 8 stamps) to the host
+extern "C" __attribute__((visibility("default"))) int srcnn_debug_tc2_timeline(srcnn_ctx* c, long long* out) {
+    if (!c || !c->work_buf.p) return SRCNN_E_ARG;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    const size_t bytes = 4 * srcnn::tc2::kDbgRows * srcnn::tc2::kDbgSlots * sizeof(long long);
+    return cudaMemcpy(out, c->work_buf.p, bytes, cudaMemcpyDeviceToHost) == cudaSuccess ? SRCNN_OK : SRCNN_E_CUDA;
+}

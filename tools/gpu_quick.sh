@@ -11,4 +11,4 @@ l=[x for x in open('gpurun_out/b_tc.log') if x.startswith('{')]
 if l:
     d=json.loads(l[-1]); print('VALUE %.0f MPix/s  ms/step %.4f  e2e %.0f  tc_ms %.4f  frac %.3f  A_ms %.4f C_ms %.4f clocks %s'%(d['value'],d['ms_per_step'],d['e2e']['value'],d['roofline']['kernel_ms'],d['roofline']['frac'],d['stages']['colour_bicubic_ms'],d['stages']['merge_ms'],d['clocks']))
 PY
-timeout 120 python tools/tc_timeline.py 2>&1 | head -14
+timeout 120 python tools/tc2_timeline.py 2>&1 | tail -60
