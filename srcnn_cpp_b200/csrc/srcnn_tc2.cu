@@ -46,10 +46,10 @@ namespace tc2 {
 // geometry
 // ---------------------------------------------------------------------------------------------
 constexpr int kStripCols = 124;                   // valid output columns per strip = TMEM lanes 2..125
-constexpr int kSlots = 10;                        // im2col ring: 10 image rows x 5 TMEM columns (9 taps + pad)
+constexpr int kSlots = 11;                        // im2col ring: 11 image rows x 5 TMEM columns (9 taps + pad)
 constexpr int kSlotCols = 5;
 constexpr int kC1Chunks = 7;                      // conv1 K = 112 = 7 x 16  (56 TMEM columns)
-constexpr int kOnesCol = 50;                      // ring column holding (1.0, 1.0): bias rows of conv1 / conv2
+constexpr int kOnesCol = 55;                      // ring column holding (1.0, 1.0): bias rows of conv1 / conv2
 constexpr int kUnits = 3;                         // rows in flight per pipeline
 constexpr int kUnitCols = 64;
 constexpr int kRingOff = kUnits * kUnitCols;      // ring columns [192, 248) of the pipeline's 256
@@ -71,10 +71,10 @@ constexpr int kImgB3 = kImgB2 + kB2Bytes;
 constexpr int kOffY = kOffW + kWeightBytes;
 constexpr int kOffHx = kOffY + 2 * kYSlots * kYRowBytes;
 constexpr int kOffBar = kOffHx + 2 * kHxBytes;
-constexpr int kBarsPerPipe = 35;                  // D1full[3] D2full[3] Tfull[3] | A1ready[3] A2ready[3] unitfree[3] | ringready[16] | hx
+constexpr int kBarsPerPipe = 19;                  // D1full[3] D2full[3] Tfull[3] | A1ready[3] A2ready[3] unitfree[3] | hx
 constexpr int kOffTmem = kOffBar + 8 + 2 * kBarsPerPipe * 8;
 constexpr int kSmemBytes = kOffTmem + 64;
-constexpr int kThreads = 896;                     // 2 x (E1, E2+producer, E3) warpgroups + one issuer warpgroup
+constexpr int kThreads = 1024;                    // 2 pipelines x (E1, producer, E3, E2) warpgroups
 static_assert(kWeightBytes % 64 == 0 && kSmemBytes <= 227 * 1024, "shared memory budget");
 
 __constant__ float c_b3;
@@ -115,12 +115,14 @@ __device__ __forceinline__ uint32_t mbar_try_wait_hint(uint32_t bar, uint32_t pa
         : "memory");
     return ok;
 }
-// bounded wait: a protocol bug must surface as an error code, never as a hung GPU
+// bounded wait: a protocol bug must surface as an error code, never as a hung GPU.
+// Plain try_wait: the hardware parks the warp until the phase completes or its own time limit passes (no issue slots
+// used meanwhile).  The suspend-time-hint form compiles to a NANOSLEEP.SYNCS loop that wakes on EVERY barrier event of
+// the CTA: ncu counted 18 wake-ups per wait, 28 % of all executed instructions, in the highest-priority warps.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* guard, int code) {
-    if (mbar_try_wait(bar, parity)) return;
     uint32_t tries = 0;
-    while (!mbar_try_wait_hint(bar, parity, 20000u)) {
-        if (++tries > 100000u) {   // >> any legitimate wait (each try parks for up to 20 us)
+    while (!mbar_try_wait(bar, parity)) {
+        if (++tries > (1u << 24)) {   // seconds: >> any legitimate wait
             *guard = code;
             __threadfence_system();
             __trap();
@@ -141,6 +143,12 @@ __device__ __forceinline__ uint32_t elect_one() {
     uint32_t pred;
     asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.b32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
     return pred;
+}
+// one arrive per WARP (barrier count 4 per warpgroup): every lane has fenced its own TMEM / shared-memory writes, the
+// warp converges, one lane signals.  128 single-thread arrives per phase wake every parked waiter of the CTA 128 times.
+__device__ __forceinline__ void warp_arrive(uint32_t bar, uint32_t leader) {
+    __syncwarp();
+    if (leader) mbar_arrive(bar);
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
@@ -164,6 +172,19 @@ __device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a_tmem, uint64_t b, 
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d),
         "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// same, with the 64-bit shared-memory descriptor given as its two words: consecutive K steps of one operand image
+// differ only by an add on the low word (address field), so an issue loop costs one uniform add per MMA
+__device__ __forceinline__ uint32_t desc_lo(uint32_t addr, uint32_t lbo_bytes) {
+    return ((addr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16);
+}
+__host__ __device__ constexpr uint32_t desc_hi(uint32_t sbo_bytes) { return (sbo_bytes >> 4) | (1u << 14); }
+__device__ __forceinline__ void mma_ts2(uint32_t d, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 bd;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b64 bd, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], bd, %4, p;\n\t}" ::"r"(d),
+        "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc)
         : "memory");
 }
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
@@ -242,7 +263,7 @@ constexpr int kDbgRows = 64, kDbgSlots = 8;
 #define TL2(role_, row_, slot_)                                                                                   \
     do {                                                                                                          \
         if constexpr (DBG)                                                                                        \
-            if (blockIdx.x == 0 && pipe == 0 && (ROLE >= 3 ? (threadIdx.x & 31) == 0 : tp == 0) && first_seg &&  \
+            if (blockIdx.x == 0 && pipe == 0 && tp == 0 && first_seg &&  \
                 (row_) >= 0 && (row_) < kDbgRows)                                                                 \
                 p.dbg[(((role_) * kDbgRows) + (row_)) * kDbgSlots + (slot_)] = clock64();                        \
     } while (0)
@@ -254,6 +275,13 @@ struct UnitCursor {
         if (++u == (uint32_t)kUnits) { u = 0; par ^= 1u; }
     }
 };
+__device__ __forceinline__ void st_shared_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_shared_u16(uint32_t addr, unsigned short v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory"); }
 // same for the sixteen ring-row barriers
 struct RingCursor {
     uint32_t idx = 0, par = 0;
@@ -271,28 +299,35 @@ struct RingCursor {
 // ---- E3 helpers (free functions with explicit state: the five phases of the row ring inline without spills) ----
 struct E3Ctx {
     const Params& p;
-    float* hx;
+    uint32_t hx_w;         // shared address of this lane's slot in exchange plane 0 of buffer 0
     uint32_t hxbar, bars, tml;
-    int x, tp, pipe, ta, tb, ra, rb;
+    int tp, pipe, ta, tb, ra, rb;
     bool col_ok, first_seg;
+    uint32_t leader;
 };
+constexpr uint32_t kHxBuf = 5 * 128 * 4;   // one exchange buffer: [n][lane] fp32
 // store the row that was published to the horizontal exchange one step ago
-__device__ __forceinline__ void e3_emit(const E3Ctx& c, const int (&ln)[5], const uint32_t npub, int& pend_r) {
+__device__ __forceinline__ void e3_emit(const E3Ctx& c, const uint32_t (&hx_r)[5], const uint32_t npub, int& pend_r, uint8_t*& outp) {
     const uint32_t k = npub - 1u;
     mbar_wait(c.hxbar, k & 1u, c.p.guard, 41);         // all 128 lanes have published row pend_r
-    const float* hb = c.hx + (k & 1u) * (5 * 128);
-    float sum = hb[0 * 128 + ln[0]];
+    const uint32_t bo = (k & 1u) * kHxBuf;
+    float v[5];
 #pragma unroll
-    for (int n = 1; n < 5; n++) sum += hb[n * 128 + ln[n]];
+    for (int n = 0; n < 5; n++) v[n] = ld_shared_f32(hx_r[n] + bo);
+    float sum = v[0];
+#pragma unroll
+    for (int n = 1; n < 5; n++) sum += v[n];
     sum += c_b3;                                // src/srcnn.cpp:235
     int q = (int)sum;                           // :238 truncation toward zero
     q = min(max(q, 0), 255);
-    if (c.col_ok) c.p.out[(size_t)(pend_r - c.p.row0) * c.p.out_pitch + c.x] = (uint8_t)q;
+    if (c.col_ok) *outp = (uint8_t)q;
+    outp += c.p.out_pitch;
     pend_r = -1;
 }
 // one T row: acc[k] = pending output row rho-2+k (the window slides down one row per step)
 template <bool DBG>
-__device__ __forceinline__ void e3_step(const E3Ctx& c, const int (&ln)[5], float (&acc)[5][5], const int rho, UnitCursor& uc, uint32_t& npub, int& pend_r) {
+__device__ __forceinline__ void e3_step(const E3Ctx& c, const uint32_t (&hx_r)[5], float (&acc)[5][5], const int rho, UnitCursor& uc,
+                                        uint32_t& npub, int& pend_r, uint8_t*& outp) {
     constexpr int ROLE = 2;
     const Params& p = c.p;
     const int pipe = c.pipe, tp = c.tp;
@@ -302,19 +337,20 @@ __device__ __forceinline__ void e3_step(const E3Ctx& c, const int (&ln)[5], floa
     uint32_t tv[25];   // the 25 taps: three loads (16 + 8 + 1 columns) instead of one 32-register block
     TL2(2, rho - c.ta, 0);
     if (has_t) {
-        mbar_wait(c.bars + (6 + uc.u) * 8, uc.par, p.guard, 40);   // TFULL
+        mbar_wait(c.bars + 48 + uc.u * 8, uc.par, p.guard, 40);   // TFULL
         tc_fence_after();
-        tmem_ld16(c.tml + uc.u * kUnitCols, tv);     // in flight while the previous row is stored
-        tmem_ld8(c.tml + uc.u * kUnitCols + 16, tv + 16);
-        tmem_ld1(c.tml + uc.u * kUnitCols + 24, tv[24]);
+        const uint32_t t = c.tml + uc.u * kUnitCols;
+        tmem_ld16(t, tv);     // in flight while the previous row is stored
+        tmem_ld8(t + 16, tv + 16);
+        tmem_ld1(t + 24, tv[24]);
     }
     TL2(2, rho - c.ta, 1);
-    if (pend_r >= 0) e3_emit(c, ln, npub, pend_r);
+    if (pend_r >= 0) e3_emit(c, hx_r, npub, pend_r, outp);
     TL2(2, rho - c.ta, 2);
     if (has_t) {
         tc_wait_ld();
         tc_fence_before();
-        mbar_arrive(c.bars + (15 + uc.u) * 8);       // UNITFREE
+        warp_arrive(c.bars + 120 + uc.u * 8, c.leader);       // UNITFREE
         uc.next();
         // T[m*5+n] belongs to output row rho - (m-2): window position k = 4 - m
 #pragma unroll
@@ -339,10 +375,10 @@ __device__ __forceinline__ void e3_step(const E3Ctx& c, const int (&ln)[5], floa
     TL2(2, rho - c.ta, 3);
     const int r = rho - 2;
     if (r >= c.ra && r < c.rb) {       // output row r is complete: publish its five horizontal-tap partial sums
-        float* hb = c.hx + (npub & 1u) * (5 * 128);
+        const uint32_t w = c.hx_w + (npub & 1u) * kHxBuf;
 #pragma unroll
-        for (int n = 0; n < 5; n++) hb[n * 128 + tp] = acc[0][n];
-        mbar_arrive(c.hxbar);
+        for (int n = 0; n < 5; n++) st_shared_f32(w + n * 512, acc[0][n]);
+        warp_arrive(c.hxbar, c.leader);
         npub++;
         pend_r = r;
     }
@@ -357,7 +393,8 @@ __device__ __forceinline__ void e3_step(const E3Ctx& c, const int (&ln)[5], floa
 
 // One role's whole life: the segment loop of a pipeline.  Each role sits in its own branch of the kernel so that its
 // setmaxnreg governs the register allocation of exactly its code.
-//   ROLE 0: E1 + E2   1: im2col ring producer   2: E3   3: conv1 issuer   4: conv2 + conv3 issuer
+//   ROLE 0: E1 (+ issues conv2)   1: im2col ring producer (+ issues conv1)   2: E3   3: E2 (+ issues conv3)
+// The MMAs of a stage are issued by one elected lane of warp 0 of the warpgroup that produced their A operand.
 template <int ROLE, bool DBG>
 __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const uint32_t sbase, const uint32_t wbar, const uint32_t bars,
                                           const uint32_t tm, const uint32_t tml, const uint32_t ring, const int pipe, const int tp) {
@@ -367,21 +404,19 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
     auto A1READY = [&](uint32_t u) { return bars + (9 + u) * 8; };
     auto A2READY = [&](uint32_t u) { return bars + (12 + u) * 8; };
     auto UNITFREE = [&](uint32_t u) { return bars + (15 + u) * 8; };
-    auto RINGREADY = [&](uint32_t idx) { return bars + (18 + idx) * 8; };
-    const uint32_t HXBAR = bars + 34 * 8;
+    const uint32_t HXBAR = bars + 18 * 8;
     const int W = p.W, H = p.H;
     const int Hb = p.out_end - p.out_begin;
     const long long nworkers = (long long)gridDim.x * 2;
     const long long wk = (long long)blockIdx.x * 2 + pipe;
     long long lin = p.total * wk / nworkers;
     const long long lin_end = p.total * (wk + 1) / nworkers;
-    const int segbar = 8 + pipe;     // named barrier that closes a segment (3 warpgroups + the two issuer warps)
+    const int segbar = 8 + pipe;     // named barrier that closes a segment (the pipeline's four warpgroups)
     bool first_seg = true;
     (void)first_seg;
 
     // barrier cursors run on across segments (every row / ring row arrives exactly once on its barrier)
     UnitCursor uc, uc2;              // uc: this role's main row cursor; uc2: second stage of the role (E2 / conv3 / ring-free)
-    RingCursor rc;                   // producer: ring row being written; conv1 issuer: ring row being waited for
     uint32_t rows_done = 0;          // conv1 issuer: rows issued so far (the first three find their unit free)
     uint32_t npub = 0;               // E3: rows published to the horizontal exchange so far
     (void)rows_done; (void)npub;
@@ -397,7 +432,11 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
         tmem_st1(tml + kRingOff + kOnesCol, 0x3C003C00u);
         tc_wait_st();
     }
-    if constexpr (ROLE >= 3) mbar_wait(wbar, 0, p.guard, 1);   // packed operands have landed in shared memory
+    const uint32_t b1lo = desc_lo(sbase + kOffW, 1024), b2lo = desc_lo(sbase + kImgB2, 512), b3lo = desc_lo(sbase + kImgB3, 512);
+    (void)b1lo; (void)b2lo; (void)b3lo;
+    const bool warp0 = (tp >> 5) == 0;      // warp 0 of the warpgroup also issues the stage's MMAs (warp-uniform)
+    const uint32_t leader = elect_one();
+    if (ROLE != 2 && warp0) mbar_wait(wbar, 0, p.guard, 1);   // packed operands have landed in shared memory
 
     while (lin < lin_end) {
         // ---- one segment: strip `strip`, output rows [ra, rb) ----
@@ -410,128 +449,96 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
         const int ta = max(ra - 2, 0), tb = min(rb + 1, H - 1);   // act2 / T rows of the segment (image rows)
         const int nT = tb - ta + 1;                               // >= 1
         const int nP = nT + 8;                                    // ring rows: virtual image rows ta-4 .. tb+4
-        // ring slot by ABSOLUTE image row (virtual row v -> slot (v + 10) mod 10): a row's conv1 always sees the same K
+        // ring slot by ABSOLUTE image row (virtual row v -> slot (v + 11) mod 11): a row's conv1 always sees the same K
         // order, so results do not depend on how the image was cut into segments or bands
-        const uint32_t slot0 = (uint32_t)((ta + 6) % kSlots);
+        const uint32_t slot0 = (uint32_t)((ta - 4 + kSlots) % kSlots);
 
-        if constexpr (ROLE == 3) {
-            // ================= conv1 issuer (one elected lane): D1[u] = ring x W1[rotation] =================
-            const uint32_t leader = elect_one();
-            uint32_t rot = slot0;                 // rotation = slot of the window's first ring row
-            rc.advance(8);                        // conv1 of row i needs ring rows i .. i+8: wait for the last one
+        if constexpr (ROLE == 0) {
+            // ================= E1(i): D1 (64 ch fp32) -> ReLU, FP16 -> A1 (32 columns, in place); then conv2(i) ==========
             for (int i = 0; i < nT; i++) {
-                TL2(3, i, 0);
-                // sixteen barriers: the issuer skips the first eight ring rows of a segment, and a parity wait is only sound
-                // when every earlier phase of ITS barrier is already complete (rows q-16, q-32, ... are)
-                mbar_wait(RINGREADY(rc.idx), rc.par, p.guard, 10);
-                TL2(3, i, 1);
-                if (rows_done >= 3u) mbar_wait(UNITFREE(uc.u), uc.par ^ 1u, p.guard, 11);   // E3 has read T of row g-3
+                const uint32_t un = tml + uc.u * kUnitCols;
+                TL2(0, i, 0);
+                mbar_wait(D1FULL(uc.u), uc.par, p.guard, 20);
                 tc_fence_after();
-                TL2(3, i, 2);
-                if (leader) {
-                    const uint32_t d = tm + uc.u * kUnitCols;
-                    const uint32_t b = sbase + kOffW + rot * kB1Var;
+                TL2(0, i, 1);
+                // four 16-column chunks, software-pipelined: chunk k+1 is in flight while chunk k is packed
+                uint32_t va[16], vb[16], r[8];
+                tmem_ld16(un, va);
+                tc_wait_ld();
+                tmem_ld16(un + 16, vb);
 #pragma unroll
-                    for (int ch = 0; ch < kC1Chunks; ch++)
-                        mma_ts(d, ring + ch * 8, smem_desc(b + ch * kB1Chunk, 1024, 128), idesc_f16(64), ch > 0);
-                    mma_commit(D1FULL(uc.u));
-                }
-                __syncwarp();
-                TL2(3, i, 3);
-                uc.next();
-                rc.next();
-                rows_done++;
-                if (++rot == (uint32_t)kSlots) rot = 0;
-            }
-        } else if constexpr (ROLE == 4) {
-            // ================= conv2 / conv3 issuer: conv2(i), conv3(i-1), in order =================
-            const uint32_t leader = elect_one();
-            for (int i = 0; i < nT + 1; i++) {
-                if (i < nT) {
+                for (int c = 0; c < 8; c++) r[c] = relu_pack_f16x2(__uint_as_float(va[2 * c]), __uint_as_float(va[2 * c + 1]));
+                tmem_st8(un, r);
+                tc_wait_ld();
+                tmem_ld16(un + 32, va);
+#pragma unroll
+                for (int c = 0; c < 8; c++) r[c] = relu_pack_f16x2(__uint_as_float(vb[2 * c]), __uint_as_float(vb[2 * c + 1]));
+                tmem_st8(un + 8, r);
+                tc_wait_ld();
+                tmem_ld16(un + 48, vb);
+#pragma unroll
+                for (int c = 0; c < 8; c++) r[c] = relu_pack_f16x2(__uint_as_float(va[2 * c]), __uint_as_float(va[2 * c + 1]));
+                tmem_st8(un + 16, r);
+                tc_wait_ld();
+#pragma unroll
+                for (int c = 0; c < 8; c++) r[c] = relu_pack_f16x2(__uint_as_float(vb[2 * c]), __uint_as_float(vb[2 * c + 1]));
+                tmem_st8(un + 24, r);
+                tc_wait_st();
+                tc_fence_before();
+                warp_arrive(A1READY(uc.u), leader);
+                TL2(0, i, 2);
+                if (warp0) {   // conv2(i): D2 = A1 x W2 + b2 (the ones column of the ring carries the bias)
                     mbar_wait(A1READY(uc.u), uc.par, p.guard, 12);
                     tc_fence_after();
-                    TL2(3, i, 4);
+                    TL2(0, i, 3);
                     if (leader) {
-                        const uint32_t un = tm + uc.u * kUnitCols;
+                        const uint32_t ut = tm + uc.u * kUnitCols;
 #pragma unroll
                         for (int ks = 0; ks < 4; ks++)
-                            mma_ts(un + 32, un + ks * 8, smem_desc(sbase + kImgB2 + ks * 1024, 512, 128), idesc_f16(32), ks > 0);
-                        mma_ts(un + 32, ring + 48, smem_desc(sbase + kImgB2 + 4 * 1024, 512, 128), idesc_f16(32), 1);   // + b2
+                            mma_ts2(ut + 32, ut + ks * 8, b2lo + ks * 64, desc_hi(128), idesc_f16(32), ks > 0);
+                        mma_ts2(ut + 32, ring + 48, b2lo + 4 * 64, desc_hi(128), idesc_f16(32), 1);
                         mma_commit(D2FULL(uc.u));
                     }
                     __syncwarp();
-                    uc.next();
                 }
-                if (i >= 1) {
-                    mbar_wait(A2READY(uc2.u), uc2.par, p.guard, 13);
+                uc.next();
+            }
+        } else if constexpr (ROLE == 3) {
+            // ================= E2(i): D2 (32 ch fp32 at [32,64)) -> A2 (16 columns at [32,48), in place); then conv3(i) ====
+            for (int i = 0; i < nT; i++) {
+                const uint32_t un = tml + uc.u * kUnitCols;
+                TL2(3, i, 0);
+                mbar_wait(D2FULL(uc.u), uc.par, p.guard, 21);
+                tc_fence_after();
+                TL2(3, i, 1);
+                uint32_t va[32];
+                tmem_ld32(un + 32, va);
+                tc_wait_ld();
+#pragma unroll
+                for (int c = 0; c < 16; c++) va[c] = relu_pack_f16x2(__uint_as_float(va[2 * c]), __uint_as_float(va[2 * c + 1]));
+                tmem_st16(un + 32, va);
+                tc_wait_st();
+                tc_fence_before();
+                warp_arrive(A2READY(uc.u), leader);
+                TL2(3, i, 2);
+                if (warp0) {   // conv3(i) tap GEMM: T = A2 x W3
+                    mbar_wait(A2READY(uc.u), uc.par, p.guard, 13);
                     tc_fence_after();
-                    TL2(3, i - 1, 5);
+                    TL2(3, i, 3);
                     if (leader) {
-                        const uint32_t un = tm + uc2.u * kUnitCols;
+                        const uint32_t ut = tm + uc.u * kUnitCols;
 #pragma unroll
                         for (int ks = 0; ks < 2; ks++)
-                            mma_ts(un, un + 32 + ks * 8, smem_desc(sbase + kImgB3 + ks * 1024, 512, 128), idesc_f16(32), ks > 0);
-                        mma_commit(TFULL(uc2.u));
+                            mma_ts2(ut, ut + 32 + ks * 8, b3lo + ks * 64, desc_hi(128), idesc_f16(32), ks > 0);
+                        mma_commit(TFULL(uc.u));
                     }
                     __syncwarp();
-                    uc2.next();
                 }
-            }
-        } else if constexpr (ROLE == 0) {
-            // ================= E1(i): D1 (64 ch fp32) -> ReLU, FP16 -> A1 (32 columns, in place) ==================
-            // ================= E2(i-1): D2 (32 ch fp32 at [32,64)) -> A2 (16 columns at [32,48), in place) ========
-            // merged so that E2's TMEM load flies while E1's stores drain
-            for (int i = 0; i < nT + 1; i++) {
-                const bool e1 = i < nT, e2 = i >= 1;
-                const uint32_t un1 = tml + uc.u * kUnitCols, un2 = tml + uc2.u * kUnitCols;
-                uint32_t va[32], vb[32];
-                TL2(0, i, 0);
-                if (e1) {
-                    mbar_wait(D1FULL(uc.u), uc.par, p.guard, 20);
-                    tc_fence_after();
-                    TL2(0, i, 1);
-                    tmem_ld32(un1, va);
-                    tmem_ld32(un1 + 32, vb);
-                }
-                if (e2) {
-                    mbar_wait(D2FULL(uc2.u), uc2.par, p.guard, 21);
-                    tc_fence_after();
-                }
-                TL2(0, i, 2);
-                if (e1) {
-                    tc_wait_ld();
-#pragma unroll
-                    for (int c = 0; c < 16; c++) va[c] = relu_pack_f16x2(__uint_as_float(va[2 * c]), __uint_as_float(va[2 * c + 1]));
-#pragma unroll
-                    for (int c = 0; c < 16; c++) vb[c] = relu_pack_f16x2(__uint_as_float(vb[2 * c]), __uint_as_float(vb[2 * c + 1]));
-                    tmem_st16(un1, va);
-                    tmem_st16(un1 + 16, vb);
-                }
-                TL2(0, i, 3);
-                if (e2) tmem_ld32(un2 + 32, va);
-                if (e1) {
-                    tc_wait_st();
-                    tc_fence_before();
-                    mbar_arrive(A1READY(uc.u));
-                    uc.next();
-                }
-                TL2(0, i, 4);
-                if (e2) {
-                    tc_wait_ld();
-#pragma unroll
-                    for (int c = 0; c < 16; c++) va[c] = relu_pack_f16x2(__uint_as_float(va[2 * c]), __uint_as_float(va[2 * c + 1]));
-                    tmem_st16(un2 + 32, va);
-                    tc_wait_st();
-                    tc_fence_before();
-                    mbar_arrive(A2READY(uc2.u));
-                    uc2.next();
-                }
-                TL2(0, i, 5);
+                uc.next();
             }
         } else if constexpr (ROLE == 1) {
             // ================= im2col ring producer =================
             const int ybar = 1 + pipe;
-            uint8_t* yst = smem + kOffY + pipe * (kYSlots * kYRowBytes);
             const uint32_t yst_s = sbase + kOffY + pipe * (kYSlots * kYRowBytes);
             const int xc0 = min(max(xs - 6 + tp, 0), W - 1);                 // tile column tp
             const int xc1 = min(max(xs - 6 + 128 + (tp & 7), 0), W - 1);     // tile column 128 + (tp & 7)
@@ -542,19 +549,22 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
                 v0 = yrow[xc0];
                 if (tp < 8) v1 = yrow[xc1];   // no arithmetic on the loaded values here: nothing waits for the loads
             };
+            const uint32_t st_my = yst_s + 4 + tp * 2;
             auto stage = [&](int q, uint32_t v0, uint32_t v1) {   // exact u8 -> FP16 (integers below 2048 are exact)
-                uint8_t* row = yst + (q & (kYSlots - 1)) * kYRowBytes;
-                *reinterpret_cast<__half*>(row + 4 + tp * 2) = __ushort2half_rn((unsigned short)v0);
-                if (tp < 8) *reinterpret_cast<__half*>(row + 4 + (128 + tp) * 2) = __ushort2half_rn((unsigned short)v1);
+                const uint32_t row = st_my + (q & (kYSlots - 1)) * kYRowBytes;
+                st_shared_u16(row, __half_as_ushort(__ushort2half_rn((unsigned short)v0)));
+                if (tp < 8) st_shared_u16(row + 256, __half_as_ushort(__ushort2half_rn((unsigned short)v1)));
             };
             uint32_t slot = slot0;
-            uc2 = uc;                              // ring-free cursor: conv1 of the segment's row t-10
-            // one ring row: gather 9 taps from the staged row, write the slot, stage row t+1, start loading row t+2
-            // (two register sets alternate so that a loaded value is first touched one full iteration later)
+            uint32_t rot = slot0;                  // conv1 weight rotation = slot of the window's first ring row
+            uc2 = uc;                              // ring-free cursor: conv1 of the segment's row t-11
+            // One ring row per step.  A single named barrier per row says three things at once: every lane has written ring
+            // row t (conv1 of row t-8 may be issued), row t+1 is staged in shared memory, and (warp 0 checked it) the slot of
+            // row t+1 is no longer read by any conv1.  Two register sets alternate so that a loaded Y value is first touched
+            // one full iteration after its load was issued.
             auto step = [&](int t, uint32_t& cur0, uint32_t& cur1, uint32_t& nxt0, uint32_t& nxt1) {
                 TL2(1, t, 0);
                 if (t + 2 < nP) fetch(t + 2, cur0, cur1);   // cur* held row t (already staged): free for row t+2
-                named_bar(ybar, 128);   // ring row t is staged
                 // 9 taps of lane tp = tile columns tp .. tp+8 = FP16 index 2 + tp .. of the staged row
                 const uint32_t rowaddr = yst_s + (t & (kYSlots - 1)) * kYRowBytes + 4 + ((tp >> 1) << 2);
                 uint32_t w[6], o[5];
@@ -565,40 +575,57 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
                 for (int k = 0; k < 5; k++) o[k] = __funnelshift_r(w[k], w[k + 1], sh);
                 o[4] &= 0xFFFFu;
                 TL2(1, t, 1);
-                if (t >= kSlots) {      // the slot's previous row was last read by conv1 of row t-10
-                    mbar_wait(D1FULL(uc2.u), uc2.par, p.guard, 30);
-                    tc_fence_after();
-                    uc2.next();
-                }
-                TL2(1, t, 2);
                 const uint32_t sl = tml + kRingOff + slot * kSlotCols;
                 tmem_st4(sl, o[0], o[1], o[2], o[3]);
                 tmem_st1(sl + 4, o[4]);
                 if (t + 1 < nP) stage(t + 1, nxt0, nxt1);
-                TL2(1, t, 3);
+                TL2(1, t, 2);
                 tc_wait_st();
                 tc_fence_before();
-                mbar_arrive(RINGREADY(rc.idx));
-                rc.next();
-                if (++slot == (uint32_t)kSlots) slot = 0;
+                TL2(1, t, 3);
+                if (warp0 && t + 1 >= kSlots) {   // row t+1 reuses the slot of row t+1-11, last read by conv1 of that row
+                    mbar_wait(D1FULL(uc2.u), uc2.par, p.guard, 30);
+                    uc2.next();
+                }
                 TL2(1, t, 4);
+                named_bar(ybar, 128);
+                TL2(1, t, 5);
+                if (warp0 && t >= 8) {   // conv1 of row t-8: its last ring row has just been written
+                    if (rows_done >= 3u) mbar_wait(UNITFREE(uc.u), uc.par ^ 1u, p.guard, 11);   // E3 has read T of row g-3
+                    tc_fence_after();
+                    TL2(1, t, 6);
+                    if (leader) {
+                        const uint32_t d = tm + uc.u * kUnitCols;
+                        const uint32_t b = b1lo + rot * (kB1Var >> 4);
+#pragma unroll
+                        for (int ch = 0; ch < kC1Chunks; ch++)
+                            mma_ts2(d, ring + ch * 8, b + ch * (kB1Chunk >> 4), desc_hi(128), idesc_f16(64), ch > 0);
+                        mma_commit(D1FULL(uc.u));
+                    }
+                    __syncwarp();
+                    TL2(1, t, 7);
+                    uc.next();
+                    rows_done++;
+                    if (++rot == (uint32_t)kSlots) rot = 0;
+                }
+                if (++slot == (uint32_t)kSlots) slot = 0;
             };
             uint32_t a0 = 0, a1 = 0, b0 = 0, b1 = 0;
             fetch(0, a0, a1);
             if (nP > 1) fetch(1, b0, b1);
             stage(0, a0, a1);
+            named_bar(ybar, 128);   // row 0 staged
             for (int t = 0; t < nP; t += 2) {
                 step(t, a0, a1, b0, b1);
                 if (t + 1 < nP) step(t + 1, b0, b1, a0, a1);
             }
-            for (int i = 0; i < nT; i++) uc.next();   // this role's row cursor only marks the segment start
         } else {
             // ================= E3: conv3 tap sums =================
-            float* hx = (float*)(smem + kOffHx + pipe * kHxBytes);
+            const uint32_t hx_s = sbase + kOffHx + pipe * kHxBytes;
             const int x = xs - 2 + tp;                         // image column of this lane
-            int ln[5];                                         // lanes holding act2 at clamp(x + n - 2)  (src/srcnn.cpp:209)
+            uint32_t hx_r[5];                                  // exchange slots of the lanes holding act2 at clamp(x + n - 2)  (src/srcnn.cpp:209)
 #pragma unroll
-            for (int n = 0; n < 5; n++) ln[n] = min(max(min(max(x + n - 2, 0), W - 1) - (xs - 2), 0), 127);
+            for (int n = 0; n < 5; n++) hx_r[n] = hx_s + n * 512 + 4 * min(max(min(max(x + n - 2, 0), W - 1) - (xs - 2), 0), 127);
             const bool col_ok = (tp >= 2) && (tp <= 125) && (x < W);
             float acc[5][5];                                   // ring of pending output rows x horizontal tap n
 #pragma unroll
@@ -606,23 +633,23 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
 #pragma unroll
                 for (int n = 0; n < 5; n++) acc[k][n] = 0.f;
             int pend_r = -1;                                   // row published to the exchange, not yet stored
-            E3Ctx cx{p, hx, HXBAR, bars, tml, x, tp, pipe, ta, tb, ra, rb, col_ok, first_seg};
+            uint8_t* outp = p.out + (size_t)(ra - p.row0) * p.out_pitch + x;   // rows are stored in order ra, ra+1, ...
+            E3Ctx cx{p, hx_s + 4 * tp, HXBAR, bars, tml, tp, pipe, ta, tb, ra, rb, col_ok, first_seg, leader};
             const int last = rb + 1;
-            for (int rho = ta; rho <= last; rho++) e3_step<DBG>(cx, ln, acc, rho, uc, npub, pend_r);
-            if (pend_r >= 0) e3_emit(cx, ln, npub, pend_r);
+            for (int rho = ta; rho <= last; rho++) e3_step<DBG>(cx, hx_r, acc, rho, uc, npub, pend_r, outp);
+            if (pend_r >= 0) e3_emit(cx, hx_r, npub, pend_r, outp);
         }
         first_seg = false;
-        named_bar(segbar, 3 * 128 + 64);   // segment drained: every MMA waited for, ring and units reusable from scratch
+        named_bar(segbar, 4 * 128);   // segment drained: every MMA waited for, ring and units reusable from scratch
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// the kernel: 28 warps.
-//   warpgroups 0,1 : E1 + E2 of pipeline 0,1   (D1 -> ReLU + FP16 pack -> A1, D2 -> A2; one thread per TMEM lane)
-//   warpgroups 2,3 : im2col ring producer of pipeline 0,1
-//   warpgroups 4,5 : E3 of pipeline 0,1        (tap sums, horizontal exchange, bias, truncate, clamp, store)
-//   warpgroup  6   : warp 24 / 25 = conv1 issuer of pipeline 0 / 1, warp 26 / 27 = conv2+conv3 issuer of pipeline 0 / 1
-//                    (one elected lane each)
+// the kernel: 32 warps = 8 warpgroups, one thread per TMEM lane in each.
+//   warpgroups 0,1 : E2 of pipeline 0,1        (D2 -> A2; warp 0 issues conv3)
+//   warpgroups 2,3 : E1                        (D1 -> ReLU + FP16 pack -> A1; warp 0 issues conv2)
+//   warpgroups 4,5 : E3                        (tap sums, horizontal exchange, bias, truncate, clamp, store)
+//   warpgroups 6,7 : im2col ring producer      (warp 0 issues conv1)
 // ---------------------------------------------------------------------------------------------
 template <bool DBG>
 __global__ void __launch_bounds__(kThreads, 1) k_srcnn_tc2(const Params p) {
@@ -630,11 +657,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_srcnn_tc2(const Params p) {
     const int tid = threadIdx.x;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform (see srcnn_tc.cu)
     const int wg = warp >> 2;
-    const int role = wg < 6 ? (wg >> 1) : 3;                  // 0 E1+E2, 1 producer, 2 E3, 3 issuers
-    const int pipe = wg < 6 ? (wg & 1) : (warp & 1);
+    // the warp scheduler prefers the highest warp id: the role with the longest serial chain per row gets the highest
+    // warpgroups.  wg 0,1: E2 (3)   wg 2,3: E1 (0)   wg 4,5: E3 (2)   wg 6,7: producer + conv1 issue (1)
+    const int role = (0x1203 >> ((wg >> 1) * 4)) & 0xF;
+    const int pipe = wg & 1;
     const int tp = tid & 127;                                  // TMEM lane = pixel column xs - 2 + tp
     const int quarter = warp & 3;
-    const uint32_t sbase = smem_u32(smem);
+    // the shared-window base as an opaque, provably uniform register value: left to itself the compiler rematerialises
+    // it (S2UR SR_CgaCtaId + ULEA + ...) in front of every barrier / shared-memory access of the row loops
+    uint32_t sbase = smem_u32(smem);
+    asm volatile("mov.u32 %0, %0;" : "+r"(sbase));
+    sbase = __shfl_sync(0xffffffffu, sbase, 0);
     const uint32_t wbar = sbase + kOffBar;
     const uint32_t bars = sbase + kOffBar + 8 + pipe * (kBarsPerPipe * 8);
     volatile uint32_t* tmem_slot = (volatile uint32_t*)(smem + kOffTmem);
@@ -643,7 +676,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_srcnn_tc2(const Params p) {
         mbar_init(wbar, 1);
         for (int q = 0; q < 2; q++)
             for (int i = 0; i < kBarsPerPipe; i++)
-                mbar_init(sbase + kOffBar + 8 + (q * kBarsPerPipe + i) * 8, i < 9 ? 1 : 128);
+                mbar_init(sbase + kOffBar + 8 + (q * kBarsPerPipe + i) * 8, i < 9 ? 1 : 4);   // tcgen05.commit : one arrive per warp
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(smem_u32((const void*)tmem_slot), 512);
@@ -661,19 +694,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_srcnn_tc2(const Params p) {
     const uint32_t tml = tm + ((uint32_t)(quarter * 32) << 16);         // + this warp's lane quarter
     const uint32_t ring = tm + kRingOff;
 
-    // register budget (64 512 at launch = 896 x 72): issuers 24, producer 56, E1+E2 96, E3 88
-    if (role == 3) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
-        if (warp < 26) role_loop<3, DBG>(p, smem, sbase, wbar, bars, tm, tml, ring, pipe, tp);
-        else role_loop<4, DBG>(p, smem, sbase, wbar, bars, tm, tml, ring, pipe, tp);
-    } else if (role == 1) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    // register budget (65 536 at launch = 1024 x 64): producer 48, E2 56, E1 72, E3 80
+    if (role == 1) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
         role_loop<1, DBG>(p, smem, sbase, wbar, bars, tm, tml, ring, pipe, tp);
+    } else if (role == 3) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        role_loop<3, DBG>(p, smem, sbase, wbar, bars, tm, tml, ring, pipe, tp);
     } else if (role == 0) {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 72;");
         role_loop<0, DBG>(p, smem, sbase, wbar, bars, tm, tml, ring, pipe, tp);
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 80;");
         role_loop<2, DBG>(p, smem, sbase, wbar, bars, tm, tml, ring, pipe, tp);
     }
 
@@ -704,14 +736,14 @@ int tc2_prepare_weights(Ctx* c, const float* P) {
         hi = __half2float(__float2half_rn(b));
         lo = b - hi;
     };
-    // conv1, ten rotations: for output row i (segment-local) the ring slot s holds image row i-4+j with
-    // j = (s - i mod 10) mod 10 (j = 9: a row outside the 9x9 window -> zero weights).  K index k = 10*s + tap
-    // (tap 9 = the slot's padding half), k = 100/101 = the ones column -> hi/lo halves of the bias.
+    // conv1, eleven rotations: with the window's first image row in ring slot v, slot s holds kernel row
+    // j = (s - v) mod 11 (j > 8: a row outside the 9x9 window -> zero weights).  K index k = 10*s + tap
+    // (tap 9 = the slot's padding half), k = 110/111 = the ones column -> hi/lo halves of the bias.
     for (int v = 0; v < kSlots; v++)
         for (int n = 0; n < 64; n++) {
             for (int k = 0; k < 16 * kC1Chunks; k++) {
                 float val = 0.f;
-                if (k < 100) {
+                if (k < 10 * kSlots) {
                     const int s = k / 10, tap = k % 10;
                     const int j = (s - v + kSlots) % kSlots;
                     if (j <= 8 && tap <= 8) val = w1[(n * 9 + j) * 9 + tap];

@@ -16,26 +16,25 @@ assert eng.L.srcnn_debug_tc2_timeline(eng.ctx, buf) == 0
 a = np.array(buf[:]).reshape(4, 64, 8)
 t0 = a[a > 0].min()
 lo, hi = 30, 40
-print("conv1 issuer (row i): ring wait | unitfree wait | issue 7 MMAs")
-for i in range(lo, hi):
-    r = a[3, i]
-    print(" i%2d  t=%7d  ringwait %5d  unitwait %5d  issue %4d   period %5d" % (i, r[0] - t0, r[1] - r[0], r[2] - r[1], r[3] - r[2], a[3, i + 1, 0] - r[0]))
-print("E1+E2 (iter i): D1full(i) wait | D2full(i-1) wait | wait::ld+pack+st | issue ld D2 | wait::st+arrive A1 | E2 tail")
-for i in range(lo, hi):
-    r = a[0, i]
-    print(" i%2d  t=%7d  D1wait %5d  D2wait %5d  e1 %5d  ld2 %4d  arr1 %5d  e2 %5d   period %5d" % (
-        i, r[0] - t0, r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] - r[3] if r[4] else 0, r[4] - r[3], r[5] - r[4], a[0, i + 1, 0] - r[0]))
-print("P (ring row t): fetch+bar+gather | ringfree wait | st+stage | wait::st+arrive")
+print("P (ring row t; conv1 of row t-8): fetch+gather | st+stage | wait::st | ringfree wait | named bar | unitfree wait | issue conv1")
 for i in range(lo, hi):
     r = a[1, i]
-    print(" t%2d  t=%7d  gather %5d  freewait %5d  st %5d  waitst %5d   period %5d" % (
-        i, r[0] - t0, r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] - r[3], a[1, i + 1, 0] - r[0]))
+    print(" t%2d  t=%7d  gather %5d  st %5d  waitst %5d  freew %5d  bar %5d  unitw %5d  issue %5d   period %5d" % (
+        i, r[0] - t0, r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] - r[3], r[5] - r[4], r[6] - r[5], r[7] - r[6], a[1, i + 1, 0] - r[0]))
+print("E1 (row i): D1full wait | work + arrive | wait all arrived | issue conv2")
+for i in range(lo, hi):
+    r = a[0, i]
+    print(" i%2d  t=%7d  wait %5d  work %5d  allwait %5d   period %5d" % (i, r[0] - t0, r[1] - r[0], r[2] - r[1], r[3] - r[2], a[0, i + 1, 0] - r[0]))
+print("E2 (row i): D2full wait | work + arrive | wait all arrived | issue conv3")
+for i in range(lo, hi):
+    r = a[3, i]
+    print(" i%2d  t=%7d  wait %5d  work %5d  allwait %5d   period %5d" % (i, r[0] - t0, r[1] - r[0], r[2] - r[1], r[3] - r[2], a[3, i + 1, 0] - r[0]))
 print("E3 (row): Tfull wait+ld issue | emit prev | wait::ld+arrive+acc | publish+shift")
 for i in range(lo, hi):
     r = a[2, i]
     print(" i%2d  t=%7d  wait %5d  emit %5d  acc %5d  pub %5d   period %5d" % (
         i, r[0] - t0, r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] - r[3], a[2, i + 1, 0] - r[0]))
 i = 34
-ev = [("conv1 issue", a[3, i, 2]), ("D1full seen", a[0, i, 1]), ("A1ready", a[0, i, 4]), ("conv2 issue", a[3, i, 4]),
-      ("D2 seen", a[0, i + 1, 2]), ("A2ready", a[0, i + 1, 5]), ("conv3 issue", a[3, i, 5]), ("Tfull seen", a[2, i, 1]), ("unitfree", a[2, i, 3])]
+ev = [("conv1 issue", a[1, i + 8, 6]), ("D1full seen", a[0, i, 1]), ("A1ready", a[0, i, 2]), ("conv2 issue", a[0, i, 3]),
+      ("D2 seen", a[3, i, 1]), ("A2ready", a[3, i, 2]), ("conv3 issue", a[3, i, 3]), ("Tfull seen", a[2, i, 1]), ("unitfree", a[2, i, 3])]
 print("row %d life: " % i + "  ".join("%s +%d" % (n, v - ev[0][1]) for n, v in ev))
