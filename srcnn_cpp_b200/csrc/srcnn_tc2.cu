@@ -71,8 +71,10 @@ constexpr int kImgB3 = kImgB2 + kB2Bytes;
 constexpr int kOffY = kOffW + kWeightBytes;
 constexpr int kOffHx = kOffY + 2 * kYSlots * kYRowBytes;
 constexpr int kOffBar = kOffHx + 2 * kHxBytes;
-constexpr int kBarsPerPipe = 19;                  // D1full[3] D2full[3] Tfull[3] | A1ready[3] A2ready[3] unitfree[3] | hx
-constexpr int kOffTmem = kOffBar + 8 + 2 * kBarsPerPipe * 8;
+constexpr int kBarsPerPipe = 9;                   // D1full[3] D2full[3] Tfull[3]: completion barriers of tcgen05.commit
+constexpr int kCtrBytes = 32;                     // per pipeline: freed[4] (T rows consumed, one per E3 warp), c1done, pad
+constexpr int kOffCtr = (kOffBar + 8 + 2 * kBarsPerPipe * 8 + 15) / 16 * 16;   // 16-byte aligned: freed[4] is read with one 128-bit load
+constexpr int kOffTmem = kOffCtr + 2 * kCtrBytes;
 constexpr int kSmemBytes = kOffTmem + 64;
 constexpr int kThreads = 1024;                    // 2 pipelines x (E1, producer, E3, E2) warpgroups
 static_assert(kWeightBytes % 64 == 0 && kSmemBytes <= 227 * 1024, "shared memory budget");
@@ -149,6 +151,40 @@ __device__ __forceinline__ uint32_t elect_one() {
 __device__ __forceinline__ void warp_arrive(uint32_t bar, uint32_t leader) {
     __syncwarp();
     if (leader) mbar_arrive(bar);
+}
+// Progress counters in shared memory (release store by one lane, acquire poll by the consumer): a satisfied poll is one
+// shared-memory load, a satisfied mbarrier try_wait costs ~250 cycles here.  mbarriers are kept for what only they can
+// do: receiving tcgen05.commit.
+__device__ __forceinline__ void ctr_publish(uint32_t addr, uint32_t v) {
+    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void ctr_wait_ge(uint32_t addr, uint32_t need, int* guard, int code) {
+    uint32_t v, tries = 0;
+    for (;;) {
+        asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+        if ((int)(v - need) >= 0) return;
+        if (++tries > (1u << 26)) { *guard = code; __threadfence_system(); __trap(); }
+    }
+}
+__device__ __forceinline__ void ctr_wait_ge4(uint32_t addr, uint32_t need, int* guard, int code) {   // min of four counters
+    uint32_t a, b, c, d, tries = 0;
+    for (;;) {
+        asm volatile("ld.acquire.cta.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr) : "memory");
+        if ((int)(a - need) >= 0 && (int)(b - need) >= 0 && (int)(c - need) >= 0 && (int)(d - need) >= 0) return;
+        if (++tries > (1u << 26)) { *guard = code; __threadfence_system(); __trap(); }
+    }
+}
+// A warpgroup waits for a tcgen05.commit: ONE warp polls the mbarrier, the other three park in a hardware named barrier
+// (no issue slots).  A parked try_wait returns every ~50 cycles; with all four warps of three roles polling, the polls
+// were 38 % of all executed instructions.
+__device__ __forceinline__ void wg_wait(uint32_t bar, uint32_t parity, bool poller, int barid, int* guard, int code) {
+    if (poller) {
+        mbar_wait(bar, parity, guard, code);
+        tc_fence_after();
+        tc_fence_before();
+    }
+    named_bar(barid, 128);
+    tc_fence_after();
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
@@ -300,34 +336,16 @@ struct RingCursor {
 struct E3Ctx {
     const Params& p;
     uint32_t hx_w;         // shared address of this lane's slot in exchange plane 0 of buffer 0
-    uint32_t hxbar, bars, tml;
+    uint32_t freed, bars, tml;   // freed: this warp's "T rows consumed" counter
     int tp, pipe, ta, tb, ra, rb;
-    bool col_ok, first_seg;
+    bool col_ok, first_seg, poller;
     uint32_t leader;
 };
 constexpr uint32_t kHxBuf = 5 * 128 * 4;   // one exchange buffer: [n][lane] fp32
-// store the row that was published to the horizontal exchange one step ago
-__device__ __forceinline__ void e3_emit(const E3Ctx& c, const uint32_t (&hx_r)[5], const uint32_t npub, int& pend_r, uint8_t*& outp) {
-    const uint32_t k = npub - 1u;
-    mbar_wait(c.hxbar, k & 1u, c.p.guard, 41);         // all 128 lanes have published row pend_r
-    const uint32_t bo = (k & 1u) * kHxBuf;
-    float v[5];
-#pragma unroll
-    for (int n = 0; n < 5; n++) v[n] = ld_shared_f32(hx_r[n] + bo);
-    float sum = v[0];
-#pragma unroll
-    for (int n = 1; n < 5; n++) sum += v[n];
-    sum += c_b3;                                // src/srcnn.cpp:235
-    int q = (int)sum;                           // :238 truncation toward zero
-    q = min(max(q, 0), 255);
-    if (c.col_ok) *outp = (uint8_t)q;
-    outp += c.p.out_pitch;
-    pend_r = -1;
-}
 // one T row: acc[k] = pending output row rho-2+k (the window slides down one row per step)
 template <bool DBG>
 __device__ __forceinline__ void e3_step(const E3Ctx& c, const uint32_t (&hx_r)[5], float (&acc)[5][5], const int rho, UnitCursor& uc,
-                                        uint32_t& npub, int& pend_r, uint8_t*& outp) {
+                                        uint32_t& npub, uint32_t& nfreed, uint8_t*& outp) {
     constexpr int ROLE = 2;
     const Params& p = c.p;
     const int pipe = c.pipe, tp = c.tp;
@@ -337,21 +355,21 @@ __device__ __forceinline__ void e3_step(const E3Ctx& c, const uint32_t (&hx_r)[5
     uint32_t tv[25];   // the 25 taps: three loads (16 + 8 + 1 columns) instead of one 32-register block
     TL2(2, rho - c.ta, 0);
     if (has_t) {
-        mbar_wait(c.bars + 48 + uc.u * 8, uc.par, p.guard, 40);   // TFULL
-        tc_fence_after();
+        wg_wait(c.bars + 48 + uc.u * 8, uc.par, c.poller, 10 + pipe, p.guard, 40);   // TFULL
         const uint32_t t = c.tml + uc.u * kUnitCols;
         tmem_ld16(t, tv);     // in flight while the previous row is stored
         tmem_ld8(t + 16, tv + 16);
         tmem_ld1(t + 24, tv[24]);
     }
     TL2(2, rho - c.ta, 1);
-    if (pend_r >= 0) e3_emit(c, hx_r, npub, pend_r, outp);
-    TL2(2, rho - c.ta, 2);
     if (has_t) {
         tc_wait_ld();
         tc_fence_before();
-        warp_arrive(c.bars + 120 + uc.u * 8, c.leader);       // UNITFREE
+        __syncwarp();
+        nfreed++;
+        if (c.leader) ctr_publish(c.freed, nfreed);            // the unit may be overwritten by conv1 of row +3
         uc.next();
+        TL2(2, rho - c.ta, 2);
         // T[m*5+n] belongs to output row rho - (m-2): window position k = 4 - m
 #pragma unroll
         for (int m = 0; m < 5; m++)
@@ -375,12 +393,22 @@ __device__ __forceinline__ void e3_step(const E3Ctx& c, const uint32_t (&hx_r)[5
     TL2(2, rho - c.ta, 3);
     const int r = rho - 2;
     if (r >= c.ra && r < c.rb) {       // output row r is complete: publish its five horizontal-tap partial sums
-        const uint32_t w = c.hx_w + (npub & 1u) * kHxBuf;
-#pragma unroll
-        for (int n = 0; n < 5; n++) st_shared_f32(w + n * 512, acc[0][n]);
-        warp_arrive(c.hxbar, c.leader);
+        const uint32_t bo = (npub & 1u) * kHxBuf;   // two buffers alternate: one barrier per row is enough
         npub++;
-        pend_r = r;
+#pragma unroll
+        for (int n = 0; n < 5; n++) st_shared_f32(c.hx_w + bo + n * 512, acc[0][n]);
+        named_bar(10 + pipe, 128);
+        float v[5];
+#pragma unroll
+        for (int n = 0; n < 5; n++) v[n] = ld_shared_f32(hx_r[n] + bo);
+        float sum = v[0];
+#pragma unroll
+        for (int n = 1; n < 5; n++) sum += v[n];
+        sum += c_b3;                                // src/srcnn.cpp:235
+        int q = (int)sum;                           // :238 truncation toward zero
+        q = min(max(q, 0), 255);
+        if (c.col_ok) *outp = (uint8_t)q;
+        outp += p.out_pitch;
     }
 #pragma unroll
     for (int k = 0; k < 4; k++)
@@ -401,10 +429,7 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
     auto D1FULL = [&](uint32_t u) { return bars + (0 + u) * 8; };
     auto D2FULL = [&](uint32_t u) { return bars + (3 + u) * 8; };
     auto TFULL = [&](uint32_t u) { return bars + (6 + u) * 8; };
-    auto A1READY = [&](uint32_t u) { return bars + (9 + u) * 8; };
-    auto A2READY = [&](uint32_t u) { return bars + (12 + u) * 8; };
-    auto UNITFREE = [&](uint32_t u) { return bars + (15 + u) * 8; };
-    const uint32_t HXBAR = bars + 18 * 8;
+    const uint32_t ctr = sbase + kOffCtr + pipe * kCtrBytes;   // freed[4] at +0, c1done at +16
     const int W = p.W, H = p.H;
     const int Hb = p.out_end - p.out_begin;
     const long long nworkers = (long long)gridDim.x * 2;
@@ -434,7 +459,10 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
     }
     const uint32_t b1lo = desc_lo(sbase + kOffW, 1024), b2lo = desc_lo(sbase + kImgB2, 512), b3lo = desc_lo(sbase + kImgB3, 512);
     (void)b1lo; (void)b2lo; (void)b3lo;
-    const bool warp0 = (tp >> 5) == 0;      // warp 0 of the warpgroup also issues the stage's MMAs (warp-uniform)
+    // one warp of the warpgroup also issues the stage's MMAs (warp-uniform).  Which one differs per role and pipeline so
+    // that the six issuing warps of the CTA spread over the four SM sub-partitions (warp id mod 4) instead of all
+    // landing on sub-partition 0.
+    const bool warp0 = (tp >> 5) == ((ROLE == 1 ? 0 : 2) + pipe);
     const uint32_t leader = elect_one();
     if (ROLE != 2 && warp0) mbar_wait(wbar, 0, p.guard, 1);   // packed operands have landed in shared memory
 
@@ -458,8 +486,9 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
             for (int i = 0; i < nT; i++) {
                 const uint32_t un = tml + uc.u * kUnitCols;
                 TL2(0, i, 0);
-                mbar_wait(D1FULL(uc.u), uc.par, p.guard, 20);
-                tc_fence_after();
+                wg_wait(D1FULL(uc.u), uc.par, warp0, 3 + pipe, p.guard, 20);
+                rows_done++;
+                if (warp0 && leader) ctr_publish(ctr + 16, rows_done);   // conv1 of rows_done rows complete: their oldest ring rows may go
                 TL2(0, i, 1);
                 // four 16-column chunks, software-pipelined: chunk k+1 is in flight while chunk k is packed
                 uint32_t va[16], vb[16], r[8];
@@ -485,10 +514,9 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
                 tmem_st8(un + 24, r);
                 tc_wait_st();
                 tc_fence_before();
-                warp_arrive(A1READY(uc.u), leader);
                 TL2(0, i, 2);
+                named_bar(3 + pipe, 128);   // A1 complete in all 128 lanes
                 if (warp0) {   // conv2(i): D2 = A1 x W2 + b2 (the ones column of the ring carries the bias)
-                    mbar_wait(A1READY(uc.u), uc.par, p.guard, 12);
                     tc_fence_after();
                     TL2(0, i, 3);
                     if (leader) {
@@ -508,8 +536,7 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
             for (int i = 0; i < nT; i++) {
                 const uint32_t un = tml + uc.u * kUnitCols;
                 TL2(3, i, 0);
-                mbar_wait(D2FULL(uc.u), uc.par, p.guard, 21);
-                tc_fence_after();
+                wg_wait(D2FULL(uc.u), uc.par, warp0, 5 + pipe, p.guard, 21);
                 TL2(3, i, 1);
                 uint32_t va[32];
                 tmem_ld32(un + 32, va);
@@ -519,10 +546,9 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
                 tmem_st16(un + 32, va);
                 tc_wait_st();
                 tc_fence_before();
-                warp_arrive(A2READY(uc.u), leader);
                 TL2(3, i, 2);
+                named_bar(5 + pipe, 128);   // A2 complete in all 128 lanes
                 if (warp0) {   // conv3(i) tap GEMM: T = A2 x W3
-                    mbar_wait(A2READY(uc.u), uc.par, p.guard, 13);
                     tc_fence_after();
                     TL2(3, i, 3);
                     if (leader) {
@@ -542,12 +568,19 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
             const uint32_t yst_s = sbase + kOffY + pipe * (kYSlots * kYRowBytes);
             const int xc0 = min(max(xs - 6 + tp, 0), W - 1);                 // tile column tp
             const int xc1 = min(max(xs - 6 + 128 + (tp & 7), 0), W - 1);     // tile column 128 + (tp & 7)
-            auto fetch = [&](int q, uint32_t& v0, uint32_t& v1) {   // Y of ring row q at this thread's tile columns
-                int r = min(max(ta - 4 + q, 0), H - 1);
-                r = min(max(r - p.row0, 0), p.rows - 1);
-                const uint8_t* yrow = p.y + (size_t)r * p.pitch;
-                v0 = yrow[xc0];
-                if (tp < 8) v1 = yrow[xc1];   // no arithmetic on the loaded values here: nothing waits for the loads
+            // Y of ring rows 0, 1, 2, ... at this thread's tile columns.  The plane row of ring row q is
+            // clamp(clamp(ta-4+q, 0, H-1) - row0, 0, rows-1): it advances by 0 or 1 per ring row, so the two row pointers are
+            // carried and bumped by the pitch (no 64-bit multiply in the row loop; a 65536^2 image overflows 32-bit offsets)
+            auto plane_row = [&](int q) { return min(max(min(max(ta - 4 + q, 0), H - 1) - p.row0, 0), p.rows - 1); };
+            int prow = plane_row(0);
+            const uint8_t* yp0 = p.y + (size_t)prow * p.pitch + xc0;
+            const uint8_t* yp1 = p.y + (size_t)prow * p.pitch + xc1;
+            const size_t ypitch = p.pitch;
+            auto fetch = [&](int q, uint32_t& v0, uint32_t& v1) {   // must be called with q = 0, 1, 2, ... in order
+                const int r = plane_row(q);
+                if (r != prow) { yp0 += ypitch; yp1 += ypitch; prow = r; }
+                v0 = *yp0;
+                if (tp < 8) v1 = *yp1;   // no arithmetic on the loaded values here: nothing waits for the loads
             };
             const uint32_t st_my = yst_s + 4 + tp * 2;
             auto stage = [&](int q, uint32_t v0, uint32_t v1) {   // exact u8 -> FP16 (integers below 2048 are exact)
@@ -557,14 +590,12 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
             };
             uint32_t slot = slot0;
             uint32_t rot = slot0;                  // conv1 weight rotation = slot of the window's first ring row
-            uc2 = uc;                              // ring-free cursor: conv1 of the segment's row t-11
+            const uint32_t gbase = rows_done;      // global index of the segment's first row
             // One ring row per step.  A single named barrier per row says three things at once: every lane has written ring
             // row t (conv1 of row t-8 may be issued), row t+1 is staged in shared memory, and (warp 0 checked it) the slot of
-            // row t+1 is no longer read by any conv1.  Two register sets alternate so that a loaded Y value is first touched
-            // one full iteration after its load was issued.
-            auto step = [&](int t, uint32_t& cur0, uint32_t& cur1, uint32_t& nxt0, uint32_t& nxt1) {
+            // row t+1 is no longer read by any conv1.
+            auto step = [&](int t, uint32_t& nxt0, uint32_t& nxt1) {
                 TL2(1, t, 0);
-                if (t + 2 < nP) fetch(t + 2, cur0, cur1);   // cur* held row t (already staged): free for row t+2
                 // 9 taps of lane tp = tile columns tp .. tp+8 = FP16 index 2 + tp .. of the staged row
                 const uint32_t rowaddr = yst_s + (t & (kYSlots - 1)) * kYRowBytes + 4 + ((tp >> 1) << 2);
                 uint32_t w[6], o[5];
@@ -578,20 +609,20 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
                 const uint32_t sl = tml + kRingOff + slot * kSlotCols;
                 tmem_st4(sl, o[0], o[1], o[2], o[3]);
                 tmem_st1(sl + 4, o[4]);
-                if (t + 1 < nP) stage(t + 1, nxt0, nxt1);
+                if (t + 1 < nP) stage(t + 1, nxt0, nxt1);   // loaded one full step ago
+                if (t + 2 < nP) fetch(t + 2, nxt0, nxt1);   // issued AFTER the use above: the scoreboard the conversion waits on
+                                                            // must not also count a load that has just been issued
                 TL2(1, t, 2);
                 tc_wait_st();
                 tc_fence_before();
                 TL2(1, t, 3);
-                if (warp0 && t + 1 >= kSlots) {   // row t+1 reuses the slot of row t+1-11, last read by conv1 of that row
-                    mbar_wait(D1FULL(uc2.u), uc2.par, p.guard, 30);
-                    uc2.next();
-                }
+                if (warp0 && t + 1 >= kSlots)    // row t+1 reuses the slot of row t+1-11, last read by conv1 of that row
+                    ctr_wait_ge(ctr + 16, gbase + (uint32_t)(t + 2 - kSlots), p.guard, 30);
                 TL2(1, t, 4);
                 named_bar(ybar, 128);
                 TL2(1, t, 5);
                 if (warp0 && t >= 8) {   // conv1 of row t-8: its last ring row has just been written
-                    if (rows_done >= 3u) mbar_wait(UNITFREE(uc.u), uc.par ^ 1u, p.guard, 11);   // E3 has read T of row g-3
+                    if (rows_done >= 3u) ctr_wait_ge4(ctr, rows_done - 2u, p.guard, 11);   // E3 has read T of row g-3
                     tc_fence_after();
                     TL2(1, t, 6);
                     if (leader) {
@@ -610,15 +641,12 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
                 }
                 if (++slot == (uint32_t)kSlots) slot = 0;
             };
-            uint32_t a0 = 0, a1 = 0, b0 = 0, b1 = 0;
+            uint32_t a0 = 0, a1 = 0;
             fetch(0, a0, a1);
-            if (nP > 1) fetch(1, b0, b1);
             stage(0, a0, a1);
+            if (nP > 1) fetch(1, a0, a1);
             named_bar(ybar, 128);   // row 0 staged
-            for (int t = 0; t < nP; t += 2) {
-                step(t, a0, a1, b0, b1);
-                if (t + 1 < nP) step(t + 1, b0, b1, a0, a1);
-            }
+            for (int t = 0; t < nP; t++) step(t, a0, a1);
         } else {
             // ================= E3: conv3 tap sums =================
             const uint32_t hx_s = sbase + kOffHx + pipe * kHxBytes;
@@ -632,12 +660,10 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
             for (int k = 0; k < 5; k++)
 #pragma unroll
                 for (int n = 0; n < 5; n++) acc[k][n] = 0.f;
-            int pend_r = -1;                                   // row published to the exchange, not yet stored
             uint8_t* outp = p.out + (size_t)(ra - p.row0) * p.out_pitch + x;   // rows are stored in order ra, ra+1, ...
-            E3Ctx cx{p, hx_s + 4 * tp, HXBAR, bars, tml, tp, pipe, ta, tb, ra, rb, col_ok, first_seg, leader};
+            E3Ctx cx{p, hx_s + 4 * tp, ctr + 4 * (uint32_t)(tp >> 5), bars, tml, tp, pipe, ta, tb, ra, rb, col_ok, first_seg, warp0, leader};
             const int last = rb + 1;
-            for (int rho = ta; rho <= last; rho++) e3_step<DBG>(cx, hx_r, acc, rho, uc, npub, pend_r, outp);
-            if (pend_r >= 0) e3_emit(cx, hx_r, npub, pend_r, outp);
+            for (int rho = ta; rho <= last; rho++) e3_step<DBG>(cx, hx_r, acc, rho, uc, npub, rows_done, outp);
         }
         first_seg = false;
         named_bar(segbar, 4 * 128);   // segment drained: every MMA waited for, ring and units reusable from scratch
@@ -672,11 +698,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_srcnn_tc2(const Params p) {
     const uint32_t bars = sbase + kOffBar + 8 + pipe * (kBarsPerPipe * 8);
     volatile uint32_t* tmem_slot = (volatile uint32_t*)(smem + kOffTmem);
 
+    if (tid < 16) reinterpret_cast<volatile uint32_t*>(smem + kOffCtr)[tid] = 0u;   // progress counters
     if (tid == 0) {
         mbar_init(wbar, 1);
         for (int q = 0; q < 2; q++)
             for (int i = 0; i < kBarsPerPipe; i++)
-                mbar_init(sbase + kOffBar + 8 + (q * kBarsPerPipe + i) * 8, i < 9 ? 1 : 4);   // tcgen05.commit : one arrive per warp
+                mbar_init(sbase + kOffBar + 8 + (q * kBarsPerPipe + i) * 8, 1);   // one tcgen05.commit per phase
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(smem_u32((const void*)tmem_slot), 512);
