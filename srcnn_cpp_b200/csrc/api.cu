@@ -17,6 +17,17 @@ int fail(Ctx* c, int status, const char* fmt, ...) {
         va_start(ap, fmt);
         vsnprintf(c->err, sizeof(c->err), fmt, ap);
         va_end(ap);
+        if (c->h_guard && *c->h_guard != 0) {   // a kernel watchdog tripped before the CUDA error surfaced: say which
+            size_t n = strlen(c->err);
+            n += snprintf(c->err + n, sizeof(c->err) - n, " [device watchdog code %d;", *c->h_guard);
+            for (int i = 1; i < 65 && n + 24 < sizeof(c->err); i++)   // who else was waiting, and at which row
+                if (c->h_guard[i]) n += snprintf(c->err + n, sizeof(c->err) - n, " p%d:%d@%d", (i - 1) / 32, c->h_guard[i] & 255, (c->h_guard[i] >> 8) - 1);
+            static const char* nm[3] = {"P", "E1", "E23"};   // DBG kernel: last position of every warp (stage.row)
+            for (int sl = 0; sl < 3; sl++)
+                for (int w = 0; w < 8 && n + 24 < sizeof(c->err); w++)
+                    if (c->h_guard[65 + sl * 8 + w]) n += snprintf(c->err + n, sizeof(c->err) - n, " %s%d.%d=%d.%d", nm[sl], w / 4, w % 4, c->h_guard[65 + sl * 8 + w] >> 16, c->h_guard[65 + sl * 8 + w] & 0xFFFF);
+            snprintf(c->err + n, sizeof(c->err) - n, "]");
+        }
     }
     return status;
 }
@@ -204,8 +215,8 @@ int srcnn_create(srcnn_ctx** out, int device, int variant) {
     if (srcnn_weights_blob_size != sizeof(float) * kNumParams) return bail(SRCNN_E_ARG);
     if (cudaMalloc(&c->d_params, sizeof(float) * kNumParams) != cudaSuccess) return bail(SRCNN_E_NOMEM);
     if (cudaMemcpy(c->d_params, srcnn_weights_blob, sizeof(float) * kNumParams, cudaMemcpyHostToDevice) != cudaSuccess) return bail(SRCNN_E_CUDA);
-    if (cudaHostAlloc((void**)&c->h_guard, sizeof(int), cudaHostAllocMapped) != cudaSuccess) return bail(SRCNN_E_NOMEM);
-    *c->h_guard = 0;
+    if (cudaHostAlloc((void**)&c->h_guard, 128 * sizeof(int), cudaHostAllocMapped) != cudaSuccess) return bail(SRCNN_E_NOMEM);
+    memset(c->h_guard, 0, 128 * sizeof(int));
     if (cudaHostGetDevicePointer((void**)&c->d_guard, c->h_guard, 0) != cudaSuccess) return bail(SRCNN_E_CUDA);
     int rc = tc_prepare_weights(c, (const float*)srcnn_weights_blob);
     if (rc) return bail(rc);

@@ -64,7 +64,7 @@ struct Ctx {
     bool own_stream = false;
     cudaStream_t own = nullptr;
     long long launches = 0;
-    char err[512] = {0};
+    char err[1536] = {0};
 
     float* d_params = nullptr;       // the 8129 fp32 parameters (FP32 variant reads these)
     void* d_tc_weights = nullptr;    // packed FP16 operand images for the tcgen05 kernel
