@@ -271,11 +271,11 @@ def run_ours(args, rank, world, local_rank):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": H * W * 3, "d2h_bytes_per_step": OH * OW * 3,
                     "ms_per_step": e2e_ms_step, "api": "srcnn_process_host (pinned host buffers, blocking)"},
             "gpu_launches": launches,
-            "roofline": {"bound": "tensor", "kernel": "k_srcnn_tc (fused conv1+conv2+conv3)" if args.variant != "fp32" else "k_conv99x11_strict+k_conv55_strict",
+            "roofline": {"bound": "tensor", "kernel": "k_srcnn_tc2 (fused conv1+conv2+conv3, row-walking tcgen05)" if args.variant != "fp32" else "k_conv99x11_strict+k_conv55_strict",
                          "achieved": achieved, "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16"],
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture of this
                          # command (profiles/r1_summary.md); the Y' plane it writes stays in L2 for the merge kernel
-                         "traffic": (8.93e6 if args.variant != "fp32" else None),
+                         "traffic": (8.49e6 if args.variant != "fp32" else None),
                          "peak_source": peaks["src"], "kernel_ms": k_ms,
                          "algorithmic_flop_per_launch": FLOP_PER_PX * px_step},
             "stages": {"colour_bicubic_ms": a_ms / max(1, calls), "srcnn_ms": k_ms, "merge_ms": c_ms / max(1, calls),

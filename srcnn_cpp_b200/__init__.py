@@ -264,6 +264,11 @@ class Engine:
         self._check(self.L.srcnn_stage_cnn_device(self.ctx, int(v), _dptr(y), w, h, y.stride(0), _dptr(out), out.stride(0)))
         return out
 
+    def set_tc_kernel(self, k):
+        """Test hook: 2 = row-walking tcgen05 kernel (default), 1 = first-generation kernel."""
+        self.L.srcnn_debug_set_tc_kernel.argtypes = [C.c_void_p, C.c_int]
+        self._check(self.L.srcnn_debug_set_tc_kernel(self.ctx, int(k)))
+
     def stage_conv99x11_fp32(self, y, act2):
         h, w = y.shape
         self._check(self.L.srcnn_stage_conv99x11_fp32_device(self.ctx, _dptr(y), w, h, y.stride(0), _dptr(act2)))

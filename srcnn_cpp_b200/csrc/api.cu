@@ -22,10 +22,6 @@ int fail(Ctx* c, int status, const char* fmt, ...) {
             n += snprintf(c->err + n, sizeof(c->err) - n, " [device watchdog code %d;", *c->h_guard);
             for (int i = 1; i < 65 && n + 24 < sizeof(c->err); i++)   // who else was waiting, and at which row
                 if (c->h_guard[i]) n += snprintf(c->err + n, sizeof(c->err) - n, " p%d:%d@%d", (i - 1) / 32, c->h_guard[i] & 255, (c->h_guard[i] >> 8) - 1);
-            static const char* nm[3] = {"P", "E1", "E23"};   // DBG kernel: last position of every warp (stage.row)
-            for (int sl = 0; sl < 3; sl++)
-                for (int w = 0; w < 8 && n + 24 < sizeof(c->err); w++)
-                    if (c->h_guard[65 + sl * 8 + w]) n += snprintf(c->err + n, sizeof(c->err) - n, " %s%d.%d=%d.%d", nm[sl], w / 4, w % 4, c->h_guard[65 + sl * 8 + w] >> 16, c->h_guard[65 + sl * 8 + w] & 0xFFFF);
             snprintf(c->err + n, sizeof(c->err) - n, "]");
         }
     }
@@ -260,6 +256,13 @@ int srcnn_set_variant(srcnn_ctx* c, int variant) {
     return SRCNN_OK;
 }
 int srcnn_get_variant(srcnn_ctx* c) { return c ? c->variant : SRCNN_E_ARG; }
+
+// test hook (not part of the stable ABI): 2 = row-walking tcgen05 kernel (default), 1 = first-generation kernel
+extern "C" __attribute__((visibility("default"))) int srcnn_debug_set_tc_kernel(srcnn_ctx* c, int k) {
+    if (!c || (k != 1 && k != 2)) return SRCNN_E_ARG;
+    c->tc_kernel = k;
+    return SRCNN_OK;
+}
 
 int srcnn_set_stream(srcnn_ctx* c, void* s) {
     ENTER(c);

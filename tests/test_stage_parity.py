@@ -120,6 +120,32 @@ def test_cnn_tc_within_tolerance_uniform_noise(engine, oracle, h, w):
     _tc_check(engine, oracle, rng.integers(0, 256, (h, w), dtype=np.uint8))
 
 
+@pytest.mark.parametrize("h,w", [(130, 140), (64, 5), (300, 200)])
+def test_cnn_tc_first_generation_kernel(engine, oracle, h, w):
+    """The first-generation fused kernel (srcnn_tc.cu) stays selectable and inside the same tolerance."""
+    rng = np.random.default_rng(h * 1000 + w + 7)
+    engine.set_tc_kernel(1)
+    try:
+        _tc_check(engine, oracle, rng.integers(0, 256, (h, w), dtype=np.uint8))
+    finally:
+        engine.set_tc_kernel(2)
+
+
+def test_cnn_tc_repeatable(engine, oracle):
+    """Same input twice -> identical bytes (no dependence on scheduling inside the persistent kernel)."""
+    import torch
+    import srcnn_cpp_b200 as S
+    rng = np.random.default_rng(99)
+    y = rng.integers(0, 256, (260, 300), dtype=np.uint8)
+    outs = []
+    for _ in range(3):
+        out = torch.zeros((260, 300), dtype=torch.uint8, device="cuda:0")
+        engine.stage_cnn(_dev(y), out, variant=S.VARIANT_TC)
+        engine.sync()
+        outs.append(out.cpu().numpy())
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+
+
 def test_cnn_tc_within_tolerance_natural(engine, oracle):
     rng = np.random.default_rng(21)
     img = natural_like(rng, 180, 260)

@@ -11,6 +11,6 @@ run b_ref     python bench.py --impl reference --steps 2 --warmup 3
 run b_tc      python bench.py --steps 50 --warmup 5
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 4 --warmup 3 --no-cpu > gpurun_out/prof_bench.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_srcnn_tc -s 3 -c 1 -f -o gpurun_out/prof_tc \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_srcnn_tc2 -s 3 -c 1 -f -o gpurun_out/prof_tc2 \
     python bench.py --steps 4 --warmup 3 --no-cpu >> gpurun_out/prof_bench.log 2>&1
 echo done
