@@ -70,3 +70,24 @@ def test_product_does_not_import_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle/" not in txt.replace("oracle/:", "") or f == "__init__.py" and "import oracle" not in txt, f
                 assert "import oracle" not in txt and "from oracle" not in txt and "liboracle" not in txt, f
+
+
+def test_fused_kernel_builds_without_local_memory():
+    """A register spill around an in-flight tcgen05.ld would store a register the TMEM load has not written yet
+    (DESIGN.md section 4): the production instance of the row-walking kernel must not use local memory at all, and it
+    must be sm_100a tcgen05 code (UTCHMMA = tcgen05.mma, LDTM/STTM = tcgen05.ld/st, UBLKCP = TMA bulk copy)."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    lib = os.path.join(ROOT, "srcnn_cpp_b200", "libsrcnn_b200.so")
+    res = subprocess.run([cuobjdump, "-res-usage", lib], capture_output=True, text=True).stdout
+    m = re.search(r"Function \S*k_srcnn_tc2ILb0\S*:\s*\n\s*REG:(\d+) STACK:(\d+)", res)
+    assert m, "k_srcnn_tc2<false> not found in the library"
+    assert int(m.group(2)) == 0, "k_srcnn_tc2<false> uses local memory (stack %s bytes)" % m.group(2)
+    sass = subprocess.run([cuobjdump, "-sass", "-fun", "_ZN5srcnn3tc211k_srcnn_tc2ILb0EEEvNS0_6ParamsE", lib],
+                          capture_output=True, text=True).stdout
+    for mnemonic in ("UTCHMMA", "LDTM", "STTM", "UBLKCP", "UTCBAR"):
+        assert mnemonic in sass, mnemonic + " missing from k_srcnn_tc2's SASS"
+    assert "BRA.U.ANY" not in sass.split("UTCHMMA", 1)[1], "a tcgen05.mma sits in a waterfall (non-uniform operand) loop"
