@@ -260,7 +260,8 @@ def run_ours(args, rank, world, local_rank):
         achieved = FLOP_PER_PX * px_step / (k_ms * 1e-3) / 1e12
         a_bytes = (3.0 / (SCALE * SCALE) + 3.0) * px_step  # colour+bicubic: 3/s^2 read + 3 written per output px
         a_gbs = a_bytes / ((a_ms / max(1, calls)) * 1e-3) / 1e9
-        c_gbs = 6.0 * px_step / ((c_ms / max(1, calls)) * 1e-3) / 1e9
+        fused_merge = c_ms / max(1, calls) < 5e-3     # merge + colour-back runs inside the fused kernel: no K-C launch
+        c_gbs = 0.0 if fused_merge else 6.0 * px_step / ((c_ms / max(1, calls)) * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -280,7 +281,8 @@ def run_ours(args, rank, world, local_rank):
                          "algorithmic_flop_per_launch": FLOP_PER_PX * px_step},
             "stages": {"colour_bicubic_ms": a_ms / max(1, calls), "srcnn_ms": k_ms, "merge_ms": c_ms / max(1, calls),
                        "colour_bicubic_GBs": a_gbs, "colour_bicubic_frac_hbm": a_gbs / peaks["hbm"],
-                       "merge_GBs": c_gbs, "merge_frac_hbm": c_gbs / peaks["hbm"], "hbm_peak_GBs": peaks["hbm"]},
+                       "merge_GBs": c_gbs, "merge_frac_hbm": c_gbs / peaks["hbm"], "hbm_peak_GBs": peaks["hbm"],
+                       "merge": "fused into the SRCNN kernel's last epilogue" if fused_merge else "separate launch"},
             "clocks": sampler.result(),
         }
         if world == 1 and not args.no_cpu:

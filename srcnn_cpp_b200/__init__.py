@@ -269,6 +269,11 @@ class Engine:
         self.L.srcnn_debug_set_tc_kernel.argtypes = [C.c_void_p, C.c_int]
         self._check(self.L.srcnn_debug_set_tc_kernel(self.ctx, int(k)))
 
+    def set_fuse_merge(self, on):
+        """Test hook: merge + colour-back inside the fused tcgen05 kernel, or as a separate launch (default)."""
+        self.L.srcnn_debug_set_fuse_merge.argtypes = [C.c_void_p, C.c_int]
+        self._check(self.L.srcnn_debug_set_fuse_merge(self.ctx, int(bool(on))))
+
     def stage_conv99x11_fp32(self, y, act2):
         h, w = y.shape
         self._check(self.L.srcnn_stage_conv99x11_fp32_device(self.ctx, _dptr(y), w, h, y.stride(0), _dptr(act2)))

@@ -132,9 +132,17 @@ static int process_rows(Ctx* c, const uint8_t* d_src, int w, int h, size_t src_s
     ca.row0 = p0; ca.rows = p1 - p0;
     ca.out_begin = r0; ca.out_end = r1;
     ca.out = pl.yout; ca.out_pitch = pl.pitch;
+    // optionally the row-walking tcgen05 kernel merges Cr/Cb and converts back to BGR in its last epilogue (no Y' plane, no
+    // K-C launch); measured slower than the separate launch (byte stores from one-thread-per-column lanes), so off by default
+    const bool fused = c->variant == SRCNN_VARIANT_TC && c->tc_kernel == 2 && c->fuse_merge;
+    if (fused) {
+        ca.cr = pl.cr; ca.cb = pl.cb;
+        ca.bgr = d_dst; ca.bgr_stride = dst_stride; ca.order = order;
+    }
     rc = run_cnn(c, c->variant, ca);
     if (rc) return rc;
     if ((rc = prof_mark(c))) return rc;
+    if (fused) return prof_mark(c);
 
     MergeArgs ma;
     const size_t off = (size_t)(r0 - p0) * pl.pitch;
@@ -219,6 +227,7 @@ int srcnn_create(srcnn_ctx** out, int device, int variant) {
     rc = tc2_prepare_weights(c, (const float*)srcnn_weights_blob);
     if (rc) return bail(rc);
     if (const char* k = getenv("SRCNN_TC_KERNEL")) c->tc_kernel = atoi(k) == 1 ? 1 : 2;
+    if (const char* k = getenv("SRCNN_FUSE_MERGE")) c->fuse_merge = atoi(k) != 0;
     *out = c;
     return SRCNN_OK;
 }
@@ -261,6 +270,12 @@ int srcnn_get_variant(srcnn_ctx* c) { return c ? c->variant : SRCNN_E_ARG; }
 extern "C" __attribute__((visibility("default"))) int srcnn_debug_set_tc_kernel(srcnn_ctx* c, int k) {
     if (!c || (k != 1 && k != 2)) return SRCNN_E_ARG;
     c->tc_kernel = k;
+    return SRCNN_OK;
+}
+// test hook: 1 = merge + colour-back fused into the tcgen05 kernel, 0 = separate K-C launch (default)
+extern "C" __attribute__((visibility("default"))) int srcnn_debug_set_fuse_merge(srcnn_ctx* c, int on) {
+    if (!c) return SRCNN_E_ARG;
+    c->fuse_merge = on != 0;
     return SRCNN_OK;
 }
 

@@ -70,6 +70,8 @@ struct Ctx {
     void* d_tc_weights = nullptr;    // packed FP16 operand images for the tcgen05 kernel
     size_t tc_weights_bytes = 0;
     void* d_tc2_weights = nullptr;   // same for the row-walking kernel (srcnn_tc2.cu)
+    bool fuse_merge = false;         // row-walking kernel: merge + YCrCb->BGR in its last epilogue instead of the K-C launch
+                                     // (SRCNN_FUSE_MERGE=1; byte-identical, but 0.236 vs 0.214 ms per 4K frame: off by default)
     int tc_kernel = 2;               // 2 = row-walking kernel (default), 1 = first-generation kernel (SRCNN_TC_KERNEL=1)
     int* d_guard = nullptr;          // device-side watchdog flag (mapped pinned)
     int* h_guard = nullptr;
@@ -140,6 +142,14 @@ struct CnnArgs {
     int out_begin, out_end;
     uint8_t* out;
     size_t out_pitch;
+    // optional fused merge + YCrCb->BGR (row-walking tcgen05 kernel only): when `bgr` is set the kernel reads the Cr/Cb planes
+    // (same pitch / row0 convention as y) and writes interleaved pixels for output rows [out_begin, out_end) to `bgr`
+    // (which points at row out_begin) instead of the Y' plane
+    const uint8_t* cr = nullptr;
+    const uint8_t* cb = nullptr;
+    uint8_t* bgr = nullptr;
+    size_t bgr_stride = 0;
+    int order = 0;
 };
 int launch_cnn_fp32(Ctx* c, const CnnArgs& a, float* act2_out /* optional full act2 dump, may be null */);
 int launch_cnn_tc(Ctx* c, const CnnArgs& a);

@@ -290,6 +290,11 @@ struct Params {
     int out_begin, out_end;  // image rows to produce
     uint8_t* out;          // same row0 convention as y
     size_t out_pitch;
+    const uint8_t* cr;     // fused merge (optional, bgr != nullptr): chroma planes, same pitch / row0 as y
+    const uint8_t* cb;
+    uint8_t* bgr;          // interleaved result, row out_begin first
+    size_t bgr_stride;
+    int swap_rb;           // 1: R,G,B byte order
     const uint8_t* wimg;   // packed FP16 operand image (kWeightBytes)
     long long total;       // strips x (out_end - out_begin) row steps
     int* guard;
@@ -343,9 +348,10 @@ struct E3Ctx {
 };
 constexpr uint32_t kHxBuf = 5 * 128 * 4;   // one exchange buffer: [n][lane] fp32
 // one T row: acc[k] = pending output row rho-2+k (the window slides down one row per step)
-template <bool DBG>
+// `outp`: Y' plane (plain) or interleaved result (FUSED) pointer of the next row to store; `crp` / `cbp`: chroma (FUSED)
+template <bool DBG, bool FUSED>
 __device__ __forceinline__ void e3_step(const E3Ctx& c, const uint32_t (&hx_r)[5], float (&acc)[5][5], const int rho, UnitCursor& uc,
-                                        uint32_t& npub, uint32_t& nfreed, uint8_t*& outp) {
+                                        uint32_t& npub, uint32_t& nfreed, uint8_t*& outp, const uint8_t*& crp, const uint8_t*& cbp) {
     constexpr int ROLE = 2;
     const Params& p = c.p;
     const int pipe = c.pipe, tp = c.tp;
@@ -393,6 +399,11 @@ __device__ __forceinline__ void e3_step(const E3Ctx& c, const uint32_t (&hx_r)[5
     TL2(2, rho - c.ta, 3);
     const int r = rho - 2;
     if (r >= c.ra && r < c.rb) {       // output row r is complete: publish its five horizontal-tap partial sums
+        uint32_t vcr = 128u, vcb = 128u;
+        if (FUSED && c.col_ok) {       // chroma of this pixel: in flight across the exchange
+            vcr = *crp;
+            vcb = *cbp;
+        }
         const uint32_t bo = (npub & 1u) * kHxBuf;   // two buffers alternate: one barrier per row is enough
         npub++;
 #pragma unroll
@@ -407,8 +418,25 @@ __device__ __forceinline__ void e3_step(const E3Ctx& c, const uint32_t (&hx_r)[5
         sum += c_b3;                                // src/srcnn.cpp:235
         int q = (int)sum;                           // :238 truncation toward zero
         q = min(max(q, 0), 255);
-        if (c.col_ok) *outp = (uint8_t)q;
-        outp += p.out_pitch;
+        if constexpr (FUSED) {
+            // merge + YCrCb -> BGR (src/srcnn.cpp:637-657; OpenCV's 14-bit fixed point) on the spot: Y' never
+            // goes to memory
+            if (c.col_ok) {
+                const int cr = (int)vcr - 128, cb = (int)vcb - 128;
+                const int B = min(max(q + ((cb * 29049 + 8192) >> 14), 0), 255);
+                const int G = min(max(q + ((cb * -5636 + cr * -11698 + 8192) >> 14), 0), 255);
+                const int R = min(max(q + ((cr * 22987 + 8192) >> 14), 0), 255);
+                outp[0] = (uint8_t)(p.swap_rb ? R : B);
+                outp[1] = (uint8_t)G;
+                outp[2] = (uint8_t)(p.swap_rb ? B : R);
+            }
+            outp += p.bgr_stride;
+            crp += p.pitch;
+            cbp += p.pitch;
+        } else {
+            if (c.col_ok) *outp = (uint8_t)q;
+            outp += p.out_pitch;
+        }
     }
 #pragma unroll
     for (int k = 0; k < 4; k++)
@@ -423,7 +451,7 @@ __device__ __forceinline__ void e3_step(const E3Ctx& c, const uint32_t (&hx_r)[5
 // setmaxnreg governs the register allocation of exactly its code.
 //   ROLE 0: E1 (+ issues conv2)   1: im2col ring producer (+ issues conv1)   2: E3   3: E2 (+ issues conv3)
 // The MMAs of a stage are issued by one elected lane of warp 0 of the warpgroup that produced their A operand.
-template <int ROLE, bool DBG>
+template <int ROLE, bool DBG, bool FUSED>
 __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const uint32_t sbase, const uint32_t wbar, const uint32_t bars,
                                           const uint32_t tm, const uint32_t tml, const uint32_t ring, const int pipe, const int tp) {
     auto D1FULL = [&](uint32_t u) { return bars + (0 + u) * 8; };
@@ -660,10 +688,14 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
             for (int k = 0; k < 5; k++)
 #pragma unroll
                 for (int n = 0; n < 5; n++) acc[k][n] = 0.f;
-            uint8_t* outp = p.out + (size_t)(ra - p.row0) * p.out_pitch + x;   // rows are stored in order ra, ra+1, ...
+            // rows are stored in order ra, ra+1, ...
+            uint8_t* outp = FUSED ? p.bgr + (size_t)(ra - p.out_begin) * p.bgr_stride + (size_t)3 * (col_ok ? x : 0)
+                                  : p.out + (size_t)(ra - p.row0) * p.out_pitch + x;
+            const uint8_t* crp = FUSED ? p.cr + (size_t)(ra - p.row0) * p.pitch + (col_ok ? x : 0) : nullptr;
+            const uint8_t* cbp = FUSED ? p.cb + (size_t)(ra - p.row0) * p.pitch + (col_ok ? x : 0) : nullptr;
             E3Ctx cx{p, hx_s + 4 * tp, ctr + 4 * (uint32_t)(tp >> 5), bars, tml, tp, pipe, ta, tb, ra, rb, col_ok, first_seg, warp0, leader};
             const int last = rb + 1;
-            for (int rho = ta; rho <= last; rho++) e3_step<DBG>(cx, hx_r, acc, rho, uc, npub, rows_done, outp);
+            for (int rho = ta; rho <= last; rho++) e3_step<DBG, FUSED>(cx, hx_r, acc, rho, uc, npub, rows_done, outp, crp, cbp);
         }
         first_seg = false;
         named_bar(segbar, 4 * 128);   // segment drained: every MMA waited for, ring and units reusable from scratch
@@ -677,7 +709,7 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
 //   warpgroups 4,5 : E3                        (tap sums, horizontal exchange, bias, truncate, clamp, store)
 //   warpgroups 6,7 : im2col ring producer      (warp 0 issues conv1)
 // ---------------------------------------------------------------------------------------------
-template <bool DBG>
+template <bool DBG, bool FUSED>
 __global__ void __launch_bounds__(kThreads, 1) k_srcnn_tc2(const Params p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x;
@@ -724,16 +756,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_srcnn_tc2(const Params p) {
     // register budget (65 536 at launch = 1024 x 64): producer 48, E2 56, E1 72, E3 80
     if (role == 1) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
-        role_loop<1, DBG>(p, smem, sbase, wbar, bars, tm, tml, ring, pipe, tp);
+        role_loop<1, DBG, FUSED>(p, smem, sbase, wbar, bars, tm, tml, ring, pipe, tp);
     } else if (role == 3) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-        role_loop<3, DBG>(p, smem, sbase, wbar, bars, tm, tml, ring, pipe, tp);
+        role_loop<3, DBG, FUSED>(p, smem, sbase, wbar, bars, tm, tml, ring, pipe, tp);
     } else if (role == 0) {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 72;");
-        role_loop<0, DBG>(p, smem, sbase, wbar, bars, tm, tml, ring, pipe, tp);
+        role_loop<0, DBG, FUSED>(p, smem, sbase, wbar, bars, tm, tml, ring, pipe, tp);
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 80;");
-        role_loop<2, DBG>(p, smem, sbase, wbar, bars, tm, tml, ring, pipe, tp);
+        role_loop<2, DBG, FUSED>(p, smem, sbase, wbar, bars, tm, tml, ring, pipe, tp);
     }
 
     tc_fence_before();
@@ -803,8 +835,9 @@ int tc2_prepare_weights(Ctx* c, const float* P) {
     SRCNN_CUDA(c, cudaMalloc(&c->d_tc2_weights, kWeightBytes));
     SRCNN_CUDA(c, cudaMemcpy(c->d_tc2_weights, img.data(), kWeightBytes, cudaMemcpyHostToDevice));
     SRCNN_CUDA(c, cudaMemcpyToSymbol(tc2::c_b3, P + kOffB3, sizeof(float)));
-    SRCNN_CUDA(c, cudaFuncSetAttribute(tc2::k_srcnn_tc2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    SRCNN_CUDA(c, cudaFuncSetAttribute(tc2::k_srcnn_tc2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    SRCNN_CUDA(c, cudaFuncSetAttribute(tc2::k_srcnn_tc2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    SRCNN_CUDA(c, cudaFuncSetAttribute(tc2::k_srcnn_tc2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    SRCNN_CUDA(c, cudaFuncSetAttribute(tc2::k_srcnn_tc2<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     return SRCNN_OK;
 }
 
@@ -822,6 +855,9 @@ int launch_cnn_tc2(Ctx* c, const CnnArgs& a) {
     p.row0 = a.row0; p.rows = a.rows;
     p.out_begin = a.out_begin; p.out_end = a.out_end;
     p.out = a.out; p.out_pitch = a.out_pitch;
+    p.cr = a.cr; p.cb = a.cb;
+    p.bgr = a.bgr; p.bgr_stride = a.bgr_stride;
+    p.swap_rb = a.order == SRCNN_ORDER_RGB ? 1 : 0;
     p.wimg = (const uint8_t*)c->d_tc2_weights;
     const int nstrips = (a.W + kStripCols - 1) / kStripCols;
     p.total = (long long)nstrips * (a.out_end - a.out_begin);
@@ -837,8 +873,9 @@ int launch_cnn_tc2(Ctx* c, const CnnArgs& a) {
     // one persistent CTA per SM; fewer when the image is too small to give every pipeline ~48 row steps
     long long want = (p.total + 95) / 96;
     int grid = (int)std::min<long long>(c->sm_count, std::max<long long>(1, want));
-    if (p.dbg) k_srcnn_tc2<true><<<grid, kThreads, kSmemBytes, c->stream>>>(p);
-    else k_srcnn_tc2<false><<<grid, kThreads, kSmemBytes, c->stream>>>(p);
+    if (p.bgr) k_srcnn_tc2<false, true><<<grid, kThreads, kSmemBytes, c->stream>>>(p);
+    else if (p.dbg) k_srcnn_tc2<true, false><<<grid, kThreads, kSmemBytes, c->stream>>>(p);
+    else k_srcnn_tc2<false, false><<<grid, kThreads, kSmemBytes, c->stream>>>(p);
     c->launches++;
     SRCNN_CUDA(c, cudaGetLastError());
     return SRCNN_OK;

@@ -83,10 +83,11 @@ def test_fused_kernel_builds_without_local_memory():
         pytest.skip("cuobjdump not available")
     lib = os.path.join(ROOT, "srcnn_cpp_b200", "libsrcnn_b200.so")
     res = subprocess.run([cuobjdump, "-res-usage", lib], capture_output=True, text=True).stdout
-    m = re.search(r"Function \S*k_srcnn_tc2ILb0\S*:\s*\n\s*REG:(\d+) STACK:(\d+)", res)
-    assert m, "k_srcnn_tc2<false> not found in the library"
-    assert int(m.group(2)) == 0, "k_srcnn_tc2<false> uses local memory (stack %s bytes)" % m.group(2)
-    sass = subprocess.run([cuobjdump, "-sass", "-fun", "_ZN5srcnn3tc211k_srcnn_tc2ILb0EEEvNS0_6ParamsE", lib],
+    for inst in ("ILb0ELb0", "ILb0ELb1"):    # <DBG=false, FUSED=false|true>: the two production instances
+        m = re.search(r"Function \S*k_srcnn_tc2" + inst + r"\S*:\s*\n\s*REG:(\d+) STACK:(\d+)", res)
+        assert m, "k_srcnn_tc2<%s> not found in the library" % inst
+        assert int(m.group(2)) == 0, "k_srcnn_tc2<%s> uses local memory (stack %s bytes)" % (inst, m.group(2))
+    sass = subprocess.run([cuobjdump, "-sass", "-fun", "_ZN5srcnn3tc211k_srcnn_tc2ILb0ELb1EEEvNS0_6ParamsE", lib],
                           capture_output=True, text=True).stdout
     for mnemonic in ("UTCHMMA", "LDTM", "STTM", "UBLKCP", "UTCBAR"):
         assert mnemonic in sass, mnemonic + " missing from k_srcnn_tc2's SASS"

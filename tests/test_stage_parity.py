@@ -219,3 +219,23 @@ def test_error_codes(engine):
     with pytest.raises(S.SrcnnError) as e:
         engine.process(np.zeros((4, 4), np.uint8), 2.0)
     assert e.value.status == S.E_ARG
+
+
+@pytest.mark.parametrize("h,w,scale,order", [(60, 90, 2.0, "bgr"), (77, 131, 2.0, "rgb"), (40, 52, 1.5, "bgr"), (33, 45, 3.0, "bgr")])
+def test_fused_merge_equals_separate_merge(engine, h, w, scale, order):
+    """Merge + YCrCb->BGR inside the fused kernel's last epilogue is byte-identical to the separate K-C launch."""
+    import torch
+    import srcnn_cpp_b200 as S
+    rng = np.random.default_rng(h * 31 + w)
+    img = torch.from_numpy(rng.integers(0, 256, (h, w, 3), dtype=np.uint8)).cuda()
+    ow, oh = S.out_dims(w, h, scale)
+    o = S.ORDER_RGB if order == "rgb" else S.ORDER_BGR
+    outs = []
+    for fuse in (1, 0):
+        engine.set_fuse_merge(fuse)
+        dst = torch.zeros((oh, ow, 3), dtype=torch.uint8, device="cuda:0")
+        engine.process_device(img, scale, dst, order=o)
+        engine.sync()
+        outs.append(dst.cpu().numpy())
+    engine.set_fuse_merge(0)
+    assert np.array_equal(outs[0], outs[1])
