@@ -594,8 +594,14 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
             // ================= im2col ring producer =================
             const int ybar = 1 + pipe;
             const uint32_t yst_s = sbase + kOffY + pipe * (kYSlots * kYRowBytes);
-            const int xc0 = min(max(xs - 6 + tp, 0), W - 1);                 // tile column tp
-            const int xc1 = min(max(xs - 6 + 128 + (tp & 7), 0), W - 1);     // tile column 128 + (tp & 7)
+            // Staging the next Y row (global load, u8 -> FP16, shared store) is left to the three warps that do NOT issue conv1:
+            // the issuing warp's serial chain is the pipeline's bottleneck.  96 lanes cover the 136 tile columns: s and
+            // 96 + s mod 40 (lanes 40.. repeat a column: same value, no divergence).
+            const int myq = tp >> 5, issq = pipe;                            // this warp's quarter, the issuing quarter
+            const int sidx = (myq - (myq > issq ? 1 : 0)) * 32 + (tp & 31);  // 0..95 over the staging lanes
+            const int sj1 = 96 + sidx % 40;
+            const int xc0 = min(max(xs - 6 + sidx, 0), W - 1);               // tile column sidx
+            const int xc1 = min(max(xs - 6 + sj1, 0), W - 1);                // tile column 96 + sidx mod 40
             // Y of ring rows 0, 1, 2, ... at this thread's tile columns.  The plane row of ring row q is
             // clamp(clamp(ta-4+q, 0, H-1) - row0, 0, rows-1): it advances by 0 or 1 per ring row, so the two row pointers are
             // carried and bumped by the pitch (no 64-bit multiply in the row loop; a 65536^2 image overflows 32-bit offsets)
@@ -605,16 +611,18 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
             const uint8_t* yp1 = p.y + (size_t)prow * p.pitch + xc1;
             const size_t ypitch = p.pitch;
             auto fetch = [&](int q, uint32_t& v0, uint32_t& v1) {   // must be called with q = 0, 1, 2, ... in order
+                if (warp0) return;
                 const int r = plane_row(q);
                 if (r != prow) { yp0 += ypitch; yp1 += ypitch; prow = r; }
                 v0 = *yp0;
-                if (tp < 8) v1 = *yp1;   // no arithmetic on the loaded values here: nothing waits for the loads
+                v1 = *yp1;   // no arithmetic on the loaded values here: nothing waits for the loads
             };
-            const uint32_t st_my = yst_s + 4 + tp * 2;
+            const uint32_t st_my = yst_s + 4 + sidx * 2, st_x = yst_s + 4 + sj1 * 2;
             auto stage = [&](int q, uint32_t v0, uint32_t v1) {   // exact u8 -> FP16 (integers below 2048 are exact)
-                const uint32_t row = st_my + (q & (kYSlots - 1)) * kYRowBytes;
-                st_shared_u16(row, __half_as_ushort(__ushort2half_rn((unsigned short)v0)));
-                if (tp < 8) st_shared_u16(row + 256, __half_as_ushort(__ushort2half_rn((unsigned short)v1)));
+                if (warp0) return;
+                const uint32_t ro = (q & (kYSlots - 1)) * kYRowBytes;
+                st_shared_u16(st_my + ro, __half_as_ushort(__ushort2half_rn((unsigned short)v0)));
+                st_shared_u16(st_x + ro, __half_as_ushort(__ushort2half_rn((unsigned short)v1)));
             };
             uint32_t slot = slot0;
             uint32_t rot = slot0;                  // conv1 weight rotation = slot of the window's first ring row
