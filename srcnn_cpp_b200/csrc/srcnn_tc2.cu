@@ -625,6 +625,7 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
                 st_shared_u16(st_x + ro, __half_as_ushort(__ushort2half_rn((unsigned short)v1)));
             };
             uint32_t slot = slot0;
+            uint32_t seen_f[4] = {0u, 0u, 0u, 0u}, seen_c = 0u;   // progress counters as seen one row ago
             uint32_t rot = slot0;                  // conv1 weight rotation = slot of the window's first ring row
             const uint32_t gbase = rows_done;      // global index of the segment's first row
             // One ring row per step.  A single named barrier per row says three things at once: every lane has written ring
@@ -652,13 +653,20 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
                 tc_wait_st();
                 tc_fence_before();
                 TL2(1, t, 3);
-                if (warp0 && t + 1 >= kSlots)    // row t+1 reuses the slot of row t+1-11, last read by conv1 of that row
-                    ctr_wait_ge(ctr + 16, gbase + (uint32_t)(t + 2 - kSlots), p.guard, 30);
+                if (warp0 && t + 1 >= kSlots) {  // row t+1 reuses the slot of row t+1-11, last read by conv1 of that row
+                    // (normally the counter value read one row ago already says so: no poll on the serial chain)
+                    const uint32_t need = gbase + (uint32_t)(t + 2 - kSlots);
+                    if ((int)(seen_c - need) < 0) ctr_wait_ge(ctr + 16, need, p.guard, 30);
+                }
                 TL2(1, t, 4);
                 named_bar(ybar, 128);
                 TL2(1, t, 5);
                 if (warp0 && t >= 8) {   // conv1 of row t-8: its last ring row has just been written
-                    if (rows_done >= 3u) ctr_wait_ge4(ctr, rows_done - 2u, p.guard, 11);   // E3 has read T of row g-3
+                    if (rows_done >= 3u) {   // E3 has read T of row g-3 (again: usually known from last row's look)
+                        const uint32_t need = rows_done - 2u;
+                        if ((int)(seen_f[0] - need) < 0 || (int)(seen_f[1] - need) < 0 || (int)(seen_f[2] - need) < 0 || (int)(seen_f[3] - need) < 0)
+                            ctr_wait_ge4(ctr, need, p.guard, 11);
+                    }
                     tc_fence_after();
                     TL2(1, t, 6);
                     if (leader) {
@@ -674,6 +682,11 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
                     uc.next();
                     rows_done++;
                     if (++rot == (uint32_t)kSlots) rot = 0;
+                }
+                if (warp0) {   // a look at both counters for the NEXT row; the loads are consumed a whole row later
+                    asm volatile("ld.acquire.cta.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                 : "=r"(seen_f[0]), "=r"(seen_f[1]), "=r"(seen_f[2]), "=r"(seen_f[3]) : "r"(ctr) : "memory");
+                    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(seen_c) : "r"(ctr + 16) : "memory");
                 }
                 if (++slot == (uint32_t)kSlots) slot = 0;
             };
