@@ -349,7 +349,7 @@ struct E3Ctx {
 constexpr uint32_t kHxBuf = 5 * 128 * 4;   // one exchange buffer: [n][lane] fp32
 // one T row: acc[k] = pending output row rho-2+k (the window slides down one row per step)
 // `outp`: Y' plane (plain) or interleaved result (FUSED) pointer of the next row to store; `crp` / `cbp`: chroma (FUSED)
-template <bool DBG, bool FUSED>
+template <int PH, bool DBG, bool FUSED>
 __device__ __forceinline__ void e3_step(const E3Ctx& c, const uint32_t (&hx_r)[5], float (&acc)[5][5], const int rho, UnitCursor& uc,
                                         uint32_t& npub, uint32_t& nfreed, uint8_t*& outp, const uint8_t*& crp, const uint8_t*& cbp) {
     constexpr int ROLE = 2;
@@ -367,7 +367,6 @@ __device__ __forceinline__ void e3_step(const E3Ctx& c, const uint32_t (&hx_r)[5
         tmem_ld8(t + 16, tv + 16);
         tmem_ld1(t + 24, tv[24]);
     }
-    TL2(2, rho - c.ta, 1);
     if (has_t) {
         tc_wait_ld();
         tc_fence_before();
@@ -375,28 +374,26 @@ __device__ __forceinline__ void e3_step(const E3Ctx& c, const uint32_t (&hx_r)[5
         nfreed++;
         if (c.leader) ctr_publish(c.freed, nfreed);            // the unit may be overwritten by conv1 of row +3
         uc.next();
-        TL2(2, rho - c.ta, 2);
-        // T[m*5+n] belongs to output row rho - (m-2): window position k = 4 - m
+            // T[m*5+n] belongs to output row rho - (m-2): window position k = 4 - m
 #pragma unroll
         for (int m = 0; m < 5; m++)
 #pragma unroll
-            for (int n = 0; n < 5; n++) acc[4 - m][n] += __uint_as_float(tv[m * 5 + n]);
+            for (int n = 0; n < 5; n++) acc[(4 - m + PH) % 5][n] += __uint_as_float(tv[m * 5 + n]);
         if (rho == 0) {        // rows -1, -2 clamp onto row 0 (src/srcnn.cpp:203)
 #pragma unroll
             for (int n = 0; n < 5; n++) {
-                acc[2][n] += __uint_as_float(tv[0 * 5 + n]) + __uint_as_float(tv[1 * 5 + n]);
-                acc[3][n] += __uint_as_float(tv[0 * 5 + n]);
+                acc[(2 + PH) % 5][n] += __uint_as_float(tv[0 * 5 + n]) + __uint_as_float(tv[1 * 5 + n]);
+                acc[(3 + PH) % 5][n] += __uint_as_float(tv[0 * 5 + n]);
             }
         }
         if (rho == p.H - 1) {    // rows H, H+1 clamp onto row H-1
 #pragma unroll
             for (int n = 0; n < 5; n++) {
-                acc[2][n] += __uint_as_float(tv[3 * 5 + n]) + __uint_as_float(tv[4 * 5 + n]);
-                acc[1][n] += __uint_as_float(tv[4 * 5 + n]);
+                acc[(2 + PH) % 5][n] += __uint_as_float(tv[3 * 5 + n]) + __uint_as_float(tv[4 * 5 + n]);
+                acc[(1 + PH) % 5][n] += __uint_as_float(tv[4 * 5 + n]);
             }
         }
     }
-    TL2(2, rho - c.ta, 3);
     const int r = rho - 2;
     if (r >= c.ra && r < c.rb) {       // output row r is complete: publish its five horizontal-tap partial sums
         uint32_t vcr = 128u, vcb = 128u;
@@ -407,7 +404,7 @@ __device__ __forceinline__ void e3_step(const E3Ctx& c, const uint32_t (&hx_r)[5
         const uint32_t bo = (npub & 1u) * kHxBuf;   // two buffers alternate: one barrier per row is enough
         npub++;
 #pragma unroll
-        for (int n = 0; n < 5; n++) st_shared_f32(c.hx_w + bo + n * 512, acc[0][n]);
+        for (int n = 0; n < 5; n++) st_shared_f32(c.hx_w + bo + n * 512, acc[PH % 5][n]);
         named_bar(10 + pipe, 128);
         float v[5];
 #pragma unroll
@@ -439,11 +436,7 @@ __device__ __forceinline__ void e3_step(const E3Ctx& c, const uint32_t (&hx_r)[5
         }
     }
 #pragma unroll
-    for (int k = 0; k < 4; k++)
-#pragma unroll
-        for (int n = 0; n < 5; n++) acc[k][n] = acc[k + 1][n];
-#pragma unroll
-    for (int n = 0; n < 5; n++) acc[4][n] = 0.f;
+    for (int n = 0; n < 5; n++) acc[PH % 5][n] = 0.f;   // becomes window position 4 of the next row
     TL2(2, rho - c.ta, 4);
 }
 
@@ -716,7 +709,18 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
             const uint8_t* cbp = FUSED ? p.cb + (size_t)(ra - p.row0) * p.pitch + (col_ok ? x : 0) : nullptr;
             E3Ctx cx{p, hx_s + 4 * tp, ctr + 4 * (uint32_t)(tp >> 5), bars, tml, tp, pipe, ta, tb, ra, rb, col_ok, first_seg, warp0, leader};
             const int last = rb + 1;
-            for (int rho = ta; rho <= last; rho++) e3_step<DBG, FUSED>(cx, hx_r, acc, rho, uc, npub, rows_done, outp, crp, cbp);
+            int rho = ta;
+            for (; rho + 4 <= last; rho += 5) {   // five rows per trip: the ring position is a compile-time constant
+                e3_step<0, DBG, FUSED>(cx, hx_r, acc, rho, uc, npub, rows_done, outp, crp, cbp);
+                e3_step<1, DBG, FUSED>(cx, hx_r, acc, rho + 1, uc, npub, rows_done, outp, crp, cbp);
+                e3_step<2, DBG, FUSED>(cx, hx_r, acc, rho + 2, uc, npub, rows_done, outp, crp, cbp);
+                e3_step<3, DBG, FUSED>(cx, hx_r, acc, rho + 3, uc, npub, rows_done, outp, crp, cbp);
+                e3_step<4, DBG, FUSED>(cx, hx_r, acc, rho + 4, uc, npub, rows_done, outp, crp, cbp);
+            }
+            if (rho <= last) e3_step<0, DBG, FUSED>(cx, hx_r, acc, rho++, uc, npub, rows_done, outp, crp, cbp);
+            if (rho <= last) e3_step<1, DBG, FUSED>(cx, hx_r, acc, rho++, uc, npub, rows_done, outp, crp, cbp);
+            if (rho <= last) e3_step<2, DBG, FUSED>(cx, hx_r, acc, rho++, uc, npub, rows_done, outp, crp, cbp);
+            if (rho <= last) e3_step<3, DBG, FUSED>(cx, hx_r, acc, rho++, uc, npub, rows_done, outp, crp, cbp);
         }
         first_seg = false;
         named_bar(segbar, 4 * 128);   // segment drained: every MMA waited for, ring and units reusable from scratch
