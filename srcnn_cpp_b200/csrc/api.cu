@@ -409,7 +409,12 @@ int srcnn_process_batch_host(srcnn_ctx* c, const uint8_t* src, int n, int w, int
         *e = c->pipe_events[i];
         return SRCNN_OK;
     };
-    const int bands = (n == 1 && oh >= 1024) ? 4 : 1;
+    // A single large frame is cut into up to 8 row bands; each band's source rows (with the halo its taps need) are copied
+    // in separately, so the first band computes after 1/8 of the H2D and the D2H stream (the PCIe-bound leg: 4x the H2D
+    // bytes at x2) starts early and never idles.
+    const int bands = (n == 1 && oh >= 1024) ? std::min(8, oh / 256) : 1;
+    TapTable* ty = nullptr;
+    if (bands > 1 && (rc = get_taps(c, h, oh, &ty))) return rc;
     cudaEvent_t ev_start;
     if ((rc = event_at(0, &ev_start))) return rc;
     for (int f0 = 0; f0 < n; f0 += chunk) {
@@ -420,14 +425,24 @@ int srcnn_process_batch_host(srcnn_ctx* c, const uint8_t* src, int n, int w, int
         SRCNN_CUDA(c, cudaStreamWaitEvent(c->s_in, ev_start, 0));
         SRCNN_CUDA(c, cudaStreamWaitEvent(c->s_out, ev_start, 0));
         for (int f = 0; f < m; f++) {
-            cudaEvent_t ev_in;
-            if ((rc = event_at(ei++, &ev_in))) return rc;
-            SRCNN_CUDA(c, cudaMemcpy2DAsync(ds + f * s_frame, s_row, src + (size_t)(f0 + f) * src_frame_stride, src_stride,
-                                            (size_t)w * 3, h, cudaMemcpyHostToDevice, c->s_in));
-            SRCNN_CUDA(c, cudaEventRecord(ev_in, c->s_in));
-            SRCNN_CUDA(c, cudaStreamWaitEvent(c->stream, ev_in, 0));
+            const uint8_t* hsrc = src + (size_t)(f0 + f) * src_frame_stride;
+            int copied = 0;   // source rows [0, copied) of this frame are on their way to the device
             for (int bi = 0; bi < bands; bi++) {
                 const int r0 = (int)((long long)oh * bi / bands), r1 = (int)((long long)oh * (bi + 1) / bands);
+                int s_hi = h;
+                if (bands > 1 && bi + 1 < bands) {   // last source row the band's bicubic taps touch (6-px halo in the output)
+                    const int p1 = std::min(r1 + 6, oh);
+                    s_hi = std::min(std::max(ty->h_ofs[p1 - 1] + 2, 0), h - 1) + 1;
+                }
+                if (s_hi > copied) {
+                    cudaEvent_t ev_in;
+                    if ((rc = event_at(ei++, &ev_in))) return rc;
+                    SRCNN_CUDA(c, cudaMemcpy2DAsync(ds + f * s_frame + (size_t)copied * s_row, s_row, hsrc + (size_t)copied * src_stride,
+                                                    src_stride, (size_t)w * 3, s_hi - copied, cudaMemcpyHostToDevice, c->s_in));
+                    SRCNN_CUDA(c, cudaEventRecord(ev_in, c->s_in));
+                    SRCNN_CUDA(c, cudaStreamWaitEvent(c->stream, ev_in, 0));
+                    copied = s_hi;
+                }
                 rc = process_rows(c, ds + f * s_frame, w, h, s_row, 0, h, order, scale, ow, oh, r0, r1,
                                   dd + f * d_frame + (size_t)r0 * d_row, d_row);
                 if (rc) return rc;
