@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(256) k_color_bicubic_direct(ResizeDev p) {
 // replicate border applied at load), (2) the integer horizontal pass runs once per footprint row,
 // (3) the vertical pass reads four shared-memory sums per sample and writes 4 pixels per store.
 // ------------------------------------------------------------------------------------------------
-constexpr int kTW = 64, kTH = 32;       // output tile
+constexpr int kTW = 64;                 // output tile width; the height is a template parameter (64 or 32 rows)
 constexpr int kMaxSC = 72, kMaxSR = 40; // footprint capacity (source cols / rows incl. the 3-tap apron)
 
 // round-half-even + saturate to 0..255 in one instruction (what v_round + v_pack_u do in cv::resize)
@@ -188,6 +188,7 @@ __device__ __forceinline__ uint32_t sat_u8_rn(float v) {
     return r;
 }
 
+template <int kTH>
 __global__ void __launch_bounds__(256) k_color_bicubic_tiled(ResizeDev p) {
     __shared__ __align__(16) uint8_t sP[3][kMaxSR][kMaxSC + 8];   // +8: the 3-word window read of the last quad may run past a row
     // horizontal sums kept as float: they are integers below 2^24, so the conversion is exact and is done
@@ -329,22 +330,28 @@ int launch_color_bicubic(Ctx* c, const ResizeArgs& a) {
     const int rows = a.row_end - a.row_begin;
     if (rows <= 0) return SRCNN_OK;
 
-    // does every tile's source footprint fit the tiled kernel's shared memory?
-    bool fits = true;
-    for (int dx0 = 0; dx0 < a.ow && fits; dx0 += kTW) {
+    // does every tile's source footprint fit the tiled kernel's shared memory?  (64-row tiles amortise the 3-row apron and
+    // fill the horizontal pass better: 33 vs 38 us at 1080p -> 4K; 32-row tiles cover smaller up-scales such as x1.5)
+    bool fits_x = true;
+    for (int dx0 = 0; dx0 < a.ow && fits_x; dx0 += kTW) {
         int dx1 = std::min(dx0 + kTW, a.ow);
-        if (a.tx->h_ofs[dx1 - 1] - a.tx->h_ofs[dx0] + 4 > kMaxSC) fits = false;
+        if (a.tx->h_ofs[dx1 - 1] - a.tx->h_ofs[dx0] + 4 > kMaxSC) fits_x = false;
     }
-    for (int dy0 = a.row_begin; dy0 < a.row_end && fits; dy0 += kTH) {
-        int dy1 = std::min(dy0 + kTH, a.row_end);
-        if (a.ty->h_ofs[dy1 - 1] - a.ty->h_ofs[dy0] + 4 > kMaxSR) fits = false;
-    }
+    auto fits_rows = [&](int th) {
+        for (int dy0 = a.row_begin; dy0 < a.row_end; dy0 += th) {
+            int dy1 = std::min(dy0 + th, a.row_end);
+            if (a.ty->h_ofs[dy1 - 1] - a.ty->h_ofs[dy0] + 4 > kMaxSR) return false;
+        }
+        return true;
+    };
+    const int th = !fits_x ? 0 : (fits_rows(64) ? 64 : (fits_rows(32) ? 32 : 0));
     p.quad_ok = 1;
     for (int dx = 0; dx + 3 < a.ow && p.quad_ok; dx += 4)
         if (a.tx->h_ofs[dx + 3] - a.tx->h_ofs[dx] > 4) p.quad_ok = 0;
-    if (fits) {
-        dim3 grid((a.ow + kTW - 1) / kTW, (rows + kTH - 1) / kTH);
-        k_color_bicubic_tiled<<<grid, 256, 0, c->stream>>>(p);
+    if (th) {
+        dim3 grid((a.ow + kTW - 1) / kTW, (rows + th - 1) / th);
+        if (th == 64) k_color_bicubic_tiled<64><<<grid, 256, 0, c->stream>>>(p);
+        else k_color_bicubic_tiled<32><<<grid, 256, 0, c->stream>>>(p);
     } else {
         dim3 grid((a.ow + 31) / 32, (rows + 7) / 8);
         k_color_bicubic_direct<<<grid, 256, 0, c->stream>>>(p);
