@@ -269,6 +269,11 @@ class Engine:
         self.L.srcnn_debug_set_tc_kernel.argtypes = [C.c_void_p, C.c_int]
         self._check(self.L.srcnn_debug_set_tc_kernel(self.ctx, int(k)))
 
+    def set_tc2_seg_ovh(self, ovh):
+        """Test hook: cost of opening a segment in the row-walking kernel's work cut (0 = equal row counts)."""
+        self.L.srcnn_debug_set_tc2_seg_ovh.argtypes = [C.c_void_p, C.c_int]
+        self._check(self.L.srcnn_debug_set_tc2_seg_ovh(self.ctx, int(ovh)))
+
     def set_fuse_merge(self, on):
         """Test hook: merge + colour-back inside the fused tcgen05 kernel, or as a separate launch (default)."""
         self.L.srcnn_debug_set_fuse_merge.argtypes = [C.c_void_p, C.c_int]

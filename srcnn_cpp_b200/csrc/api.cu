@@ -228,6 +228,7 @@ int srcnn_create(srcnn_ctx** out, int device, int variant) {
     if (rc) return bail(rc);
     if (const char* k = getenv("SRCNN_TC_KERNEL")) c->tc_kernel = atoi(k) == 1 ? 1 : 2;
     if (const char* k = getenv("SRCNN_FUSE_MERGE")) c->fuse_merge = atoi(k) != 0;
+    if (const char* k = getenv("SRCNN_TC2_SEG_OVH")) c->tc2_seg_ovh = std::max(0, std::min(64, atoi(k)));   // tuning aid
     *out = c;
     return SRCNN_OK;
 }
@@ -276,6 +277,18 @@ extern "C" __attribute__((visibility("default"))) int srcnn_debug_set_tc_kernel(
 extern "C" __attribute__((visibility("default"))) int srcnn_debug_set_fuse_merge(srcnn_ctx* c, int on) {
     if (!c) return SRCNN_E_ARG;
     c->fuse_merge = on != 0;
+    return SRCNN_OK;
+}
+
+// test hooks: the row-walking kernel's work cut (pure host arithmetic, callable without a GPU) and its segment-cost knob
+extern "C" __attribute__((visibility("default"))) int srcnn_debug_tc2_partition(int nstrips, int hb, int nworkers, int ovh, long long* bounds) {
+    if (nstrips <= 0 || hb <= 0 || nworkers <= 0 || !bounds) return SRCNN_E_ARG;
+    srcnn::tc2_partition(nstrips, hb, nworkers, ovh, bounds);
+    return SRCNN_OK;
+}
+extern "C" __attribute__((visibility("default"))) int srcnn_debug_set_tc2_seg_ovh(srcnn_ctx* c, int ovh) {
+    if (!c || ovh < 0 || ovh > 64) return SRCNN_E_ARG;
+    c->tc2_seg_ovh = ovh;
     return SRCNN_OK;
 }
 

@@ -55,6 +55,12 @@ struct Planes {
 
 struct TcWeights;  // srcnn_tc.cu
 
+// row-walking kernel: the cached cut of a launch's row steps over its pipelines (srcnn_tc2.cu, tc2_partition)
+struct Tc2Partition {
+    int nstrips = 0, hb = 0, nworkers = 0, ovh = -1;
+    std::vector<long long> bounds;
+};
+
 struct Ctx {
     int device = 0;
     int variant = SRCNN_VARIANT_TC;
@@ -72,6 +78,8 @@ struct Ctx {
     void* d_tc2_weights = nullptr;   // same for the row-walking kernel (srcnn_tc2.cu)
     bool fuse_merge = false;         // row-walking kernel: merge + YCrCb->BGR in its last epilogue instead of the K-C launch
                                      // (SRCNN_FUSE_MERGE=1; byte-identical, but 0.236 vs 0.214 ms per 4K frame: off by default)
+    Tc2Partition tc2_part;
+    int tc2_seg_ovh = 12;            // cost of opening a segment, in row steps (SRCNN_TC2_SEG_OVH; 0 = cut into equal row counts)
     int tc_kernel = 2;               // 2 = row-walking kernel (default), 1 = first-generation kernel (SRCNN_TC_KERNEL=1)
     int* d_guard = nullptr;          // device-side watchdog flag (mapped pinned)
     int* h_guard = nullptr;
@@ -158,6 +166,7 @@ void tc_release(Ctx* c);
 int launch_cnn_tc2(Ctx* c, const CnnArgs& a);
 int tc2_prepare_weights(Ctx* c, const float* params);
 void tc2_release(Ctx* c);
+void tc2_partition(int nstrips, int hb, int nworkers, int ovh, long long* bounds);
 
 }  // namespace srcnn
 

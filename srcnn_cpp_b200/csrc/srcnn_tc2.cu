@@ -77,6 +77,7 @@ constexpr int kOffCtr = (kOffBar + 8 + 2 * kBarsPerPipe * 8 + 15) / 16 * 16;   /
 constexpr int kOffTmem = kOffCtr + 2 * kCtrBytes;
 constexpr int kSmemBytes = kOffTmem + 64;
 constexpr int kThreads = 1024;                    // 2 pipelines x (E1, producer, E3, E2) warpgroups
+constexpr int kMaxWorkers = 2 * 152;              // pipelines of one launch (B200: 148 SMs); their ranges travel in the kernel parameters
 static_assert(kWeightBytes % 64 == 0 && kSmemBytes <= 227 * 1024, "shared memory budget");
 
 __constant__ float c_b3;
@@ -297,6 +298,7 @@ struct Params {
     int swap_rb;           // 1: R,G,B byte order
     const uint8_t* wimg;   // packed FP16 operand image (kWeightBytes)
     long long total;       // strips x (out_end - out_begin) row steps
+    long long bounds[kMaxWorkers + 1];   // pipeline w walks row steps [bounds[w], bounds[w+1]) of the strip-major order (tc2_partition)
     int* guard;
     long long* dbg;        // optional timeline (SRCNN_TC_DEBUG=1): clock64 stamps of pipeline 0 of CTA 0, first segment
 };
@@ -453,10 +455,9 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
     const uint32_t ctr = sbase + kOffCtr + pipe * kCtrBytes;   // freed[4] at +0, c1done at +16
     const int W = p.W, H = p.H;
     const int Hb = p.out_end - p.out_begin;
-    const long long nworkers = (long long)gridDim.x * 2;
-    const long long wk = (long long)blockIdx.x * 2 + pipe;
-    long long lin = p.total * wk / nworkers;
-    const long long lin_end = p.total * (wk + 1) / nworkers;
+    const int wk = (int)blockIdx.x * 2 + pipe;
+    long long lin = p.bounds[wk];
+    const long long lin_end = p.bounds[wk + 1];
     const int segbar = 8 + pipe;     // named barrier that closes a segment (the pipeline's four warpgroups)
     bool first_seg = true;
     (void)first_seg;
@@ -871,6 +872,47 @@ void tc2_release(Ctx* c) {
     c->d_tc2_weights = nullptr;
 }
 
+// Cuts the strip-major sequence of row steps (nstrips strips x hb rows) into `nworkers` contiguous ranges of about equal
+// COST.  A worker's piece of one strip (a "segment") costs its rows plus `ovh` row steps: eight ring rows and four halo
+// rows of conv1..conv3 are recomputed at the top and bottom of every segment, and the pipeline drains at its end.  Cutting
+// into equal ROW counts instead (ovh = 0) leaves every worker whose range crosses a strip boundary with two segments and
+// the whole launch waiting for them.  The smallest feasible budget per worker is found by bisection; results do not depend
+// on the cut (a row's arithmetic is independent of its segment: tests/test_stage_parity.py).
+void tc2_partition(int nstrips, int hb, int nworkers, int ovh, long long* bounds) {
+    const long long total = (long long)nstrips * hb;
+    if (ovh <= 0) {
+        for (int w = 0; w <= nworkers; w++) bounds[w] = total * w / nworkers;
+        return;
+    }
+    const int min_seg = 8;   // a shorter piece is not worth a segment of its own unless it finishes the strip
+    auto walk = [&](long long budget, long long* out) {
+        long long pos = 0;
+        for (int w = 0; w < nworkers; w++) {
+            if (out) out[w] = pos;
+            long long left = budget;
+            while (pos < total) {
+                const long long in_strip = hb - pos % hb;
+                const long long can = left - ovh;
+                if (can < std::min<long long>(min_seg, in_strip)) break;
+                const long long take = std::min(can, in_strip);
+                pos += take;
+                left -= take + ovh;
+            }
+        }
+        if (out) out[nworkers] = total;
+        return pos >= total;
+    };
+    long long lo = (total + nworkers - 1) / nworkers + ovh - 1, hi = lo + 1;   // lo: infeasible or unknown, hi: feasible
+    while (!walk(hi, nullptr)) { lo = hi; hi += std::max<long long>(1, hi / 8); }
+    while (hi - lo > 1) {
+        const long long mid = lo + (hi - lo) / 2;
+        if (walk(mid, nullptr)) hi = mid; else lo = mid;
+    }
+    walk(hi, bounds);
+    // the last worker took what was left; anything the greedy walk could not place (never happens for a feasible budget)
+    // would show as bounds[nworkers] < total, which the walk above rules out
+}
+
 int launch_cnn_tc2(Ctx* c, const CnnArgs& a) {
     using namespace tc2;
     if (a.out_end <= a.out_begin) return SRCNN_OK;
@@ -897,7 +939,17 @@ int launch_cnn_tc2(Ctx* c, const CnnArgs& a) {
     }
     // one persistent CTA per SM; fewer when the image is too small to give every pipeline ~48 row steps
     long long want = (p.total + 95) / 96;
-    int grid = (int)std::min<long long>(c->sm_count, std::max<long long>(1, want));
+    int grid = (int)std::min<long long>(std::min(c->sm_count, kMaxWorkers / 2), std::max<long long>(1, want));
+    {   // the pipelines' ranges (cached: frames of a stream and bands of a frame repeat the same geometry)
+        const int hb = a.out_end - a.out_begin;
+        Tc2Partition& pt = c->tc2_part;
+        if (pt.nstrips != nstrips || pt.hb != hb || pt.nworkers != 2 * grid || pt.ovh != c->tc2_seg_ovh) {
+            pt.bounds.resize(kMaxWorkers + 1);
+            tc2_partition(nstrips, hb, 2 * grid, c->tc2_seg_ovh, pt.bounds.data());
+            pt.nstrips = nstrips; pt.hb = hb; pt.nworkers = 2 * grid; pt.ovh = c->tc2_seg_ovh;
+        }
+        memcpy(p.bounds, pt.bounds.data(), sizeof(long long) * (2 * grid + 1));
+    }
     if (p.bgr) k_srcnn_tc2<false, true><<<grid, kThreads, kSmemBytes, c->stream>>>(p);
     else if (p.dbg) k_srcnn_tc2<true, false><<<grid, kThreads, kSmemBytes, c->stream>>>(p);
     else k_srcnn_tc2<false, false><<<grid, kThreads, kSmemBytes, c->stream>>>(p);

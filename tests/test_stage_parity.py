@@ -146,6 +146,28 @@ def test_cnn_tc_repeatable(engine, oracle):
     assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
 
 
+def test_tc_result_independent_of_work_cut(engine):
+    """The row-walking kernel's output does not depend on how its row steps are cut over the pipelines (tc2_partition):
+    equal row counts (0) and cost-aware cuts with different segment costs give identical bytes, on a frame large enough
+    for every one of the 296 pipelines to get work and for many of them to cross a strip boundary."""
+    import torch
+    import srcnn_cpp_b200 as S
+    rng = np.random.default_rng(5)
+    y = rng.integers(0, 256, (1100, 1500), dtype=np.uint8)
+    outs = []
+    try:
+        for ovh in (0, 12, 5, 40):
+            engine.set_tc2_seg_ovh(ovh)
+            out = torch.zeros(y.shape, dtype=torch.uint8, device="cuda:0")
+            engine.stage_cnn(_dev(y), out, variant=S.VARIANT_TC)
+            engine.sync()
+            outs.append(out.cpu().numpy())
+    finally:
+        engine.set_tc2_seg_ovh(12)
+    for o in outs[1:]:
+        assert np.array_equal(outs[0], o)
+
+
 def test_cnn_tc_within_tolerance_natural(engine, oracle):
     rng = np.random.default_rng(21)
     img = natural_like(rng, 180, 260)
