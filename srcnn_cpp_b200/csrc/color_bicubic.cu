@@ -131,6 +131,7 @@ struct ResizeDev {
     const int* yofs;
     const short4* ycoef;
     int simd_w;
+    unsigned long long negzero2;   // the pair (-0.0f, -0.0f), opaque to the compiler (see f2_mul_rn)
     int quad_ok;   // every aligned group of 4 output columns spans <= 4 source columns (true for any up-scale)
 };
 
@@ -185,6 +186,28 @@ constexpr int kMaxSC = 72, kMaxSR = 40; // footprint capacity (source cols / row
 __device__ __forceinline__ uint32_t sat_u8_rn(float v) {
     uint32_t r;
     asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return r;
+}
+
+// Packed FP32 pairs (sm_100 FMUL2 / FADD2 / FFMA2: two IEEE single-precision operations per issue slot).  The vertical pass
+// needs every product and every sum rounded on its own (cv::resize's SIMD body has no FMA), and ptxas contracts a
+// mul.rn.f32x2 feeding an add.rn.f32x2 into FFMA2 even though both carry an explicit rounding mode.  So a product is written
+// as fma(a, b, -0.0) -- exactly round(a*b), signed zeros included -- with the -0.0 pair coming from a kernel parameter the
+// compiler cannot see through; an FFMA2 feeding an FADD2 cannot be contracted any further.
+__device__ __forceinline__ unsigned long long f2_pack(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(unsigned long long v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ unsigned long long f2_mul_rn(unsigned long long a, unsigned long long b, unsigned long long negzero) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(negzero));
+    return r;
+}
+__device__ __forceinline__ unsigned long long f2_add_rn(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
 }
 
@@ -281,6 +304,7 @@ __global__ void __launch_bounds__(256) k_color_bicubic_tiled(ResizeDev p) {
         const int q = tid & 15, col = q * 4, dx = dx0 + col;
         if (dx < dx1) {
             const bool all_float = dx + 3 < p.simd_w && dx + 3 < dx1;
+            const unsigned long long nz = p.negzero2;
             for (int ty = tid >> 4; ty < kTH; ty += 16) {
                 const int dy = dy0 + ty;
                 if (dy >= dy1) break;
@@ -290,18 +314,34 @@ __global__ void __launch_bounds__(256) k_color_bicubic_tiled(ResizeDev p) {
                 const float b0 = __fmul_rn((float)cy.x, sc), b1 = __fmul_rn((float)cy.y, sc);
                 const float b2 = __fmul_rn((float)cy.z, sc), b3 = __fmul_rn((float)cy.w, sc);
                 const size_t o = (size_t)(dy - p.plane_row0) * p.pitch + dx;
+                const unsigned long long bb0 = f2_pack(b0, b0), bb1 = f2_pack(b1, b1), bb2 = f2_pack(b2, b2), bb3 = f2_pack(b3, b3);
 #pragma unroll
                 for (int pl = 0; pl < 3; pl++) {
+                    if (all_float) {   // two samples per instruction: v = H0*b0 + (H1*b1 + (H2*b2 + H3*b3)), each op rounded
+                        const ulonglong2 g0 = *reinterpret_cast<const ulonglong2*>(&sH[pl][sr][col]);
+                        const ulonglong2 g1 = *reinterpret_cast<const ulonglong2*>(&sH[pl][sr + 1][col]);
+                        const ulonglong2 g2 = *reinterpret_cast<const ulonglong2*>(&sH[pl][sr + 2][col]);
+                        const ulonglong2 g3 = *reinterpret_cast<const ulonglong2*>(&sH[pl][sr + 3][col]);
+                        unsigned long long va = f2_mul_rn(g3.x, bb3, nz), vb = f2_mul_rn(g3.y, bb3, nz);
+                        va = f2_add_rn(f2_mul_rn(g2.x, bb2, nz), va);
+                        vb = f2_add_rn(f2_mul_rn(g2.y, bb2, nz), vb);
+                        va = f2_add_rn(f2_mul_rn(g1.x, bb1, nz), va);
+                        vb = f2_add_rn(f2_mul_rn(g1.y, bb1, nz), vb);
+                        va = f2_add_rn(f2_mul_rn(g0.x, bb0, nz), va);
+                        vb = f2_add_rn(f2_mul_rn(g0.y, bb0, nz), vb);
+                        float v0, v1, v2, v3;
+                        f2_unpack(va, v0, v1);
+                        f2_unpack(vb, v2, v3);
+                        uint8_t* outp = (pl == 0 ? p.y : (pl == 1 ? p.cr : p.cb)) + o;
+                        *reinterpret_cast<uint32_t*>(outp) = sat_u8_rn(v0) | (sat_u8_rn(v1) << 8) | (sat_u8_rn(v2) << 16) | (sat_u8_rn(v3) << 24);
+                        continue;
+                    }
                     const float4 h0 = *reinterpret_cast<const float4*>(&sH[pl][sr][col]);
                     const float4 h1 = *reinterpret_cast<const float4*>(&sH[pl][sr + 1][col]);
                     const float4 h2 = *reinterpret_cast<const float4*>(&sH[pl][sr + 2][col]);
                     const float4 h3 = *reinterpret_cast<const float4*>(&sH[pl][sr + 3][col]);
                     uint8_t* out = (pl == 0 ? p.y : (pl == 1 ? p.cr : p.cb)) + o;
-                    if (all_float) {
-#define VT(F) sat_u8_rn(__fadd_rn(__fmul_rn(h0.F, b0), __fadd_rn(__fmul_rn(h1.F, b1), __fadd_rn(__fmul_rn(h2.F, b2), __fmul_rn(h3.F, b3)))))
-                        *reinterpret_cast<uint32_t*>(out) = VT(x) | (VT(y) << 8) | (VT(z) << 16) | (VT(w) << 24);
-#undef VT
-                    } else {  // tile edge and/or cv::resize's integer scalar tail (last ow mod 8 columns)
+                    {  // tile edge and/or cv::resize's integer scalar tail (last ow mod 8 columns)
                         const float hh[4][4] = {{h0.x, h0.y, h0.z, h0.w}, {h1.x, h1.y, h1.z, h1.w}, {h2.x, h2.y, h2.z, h2.w}, {h3.x, h3.y, h3.z, h3.w}};
                         for (int j = 0; j < 4 && dx + j < dx1; j++)
                             out[j] = (uint8_t)vertical_tap(__float2int_rn(hh[0][j]), __float2int_rn(hh[1][j]), __float2int_rn(hh[2][j]),
@@ -327,6 +367,7 @@ int launch_color_bicubic(Ctx* c, const ResizeArgs& a) {
     p.xofs = a.tx->d_ofs; p.xcoef = a.tx->d_coef;
     p.yofs = a.ty->d_ofs; p.ycoef = a.ty->d_coef;
     p.simd_w = (a.ow / 8) * 8;
+    p.negzero2 = 0x8000000080000000ull;
     const int rows = a.row_end - a.row_begin;
     if (rows <= 0) return SRCNN_OK;
 

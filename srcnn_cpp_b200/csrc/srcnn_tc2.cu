@@ -296,6 +296,7 @@ struct Params {
     uint8_t* bgr;          // interleaved result, row out_begin first
     size_t bgr_stride;
     int swap_rb;           // 1: R,G,B byte order
+    int e1_wide;           // E1 reads D1 with two 32-column loads (default) instead of four 16-column ones
     const uint8_t* wimg;   // packed FP16 operand image (kWeightBytes)
     long long total;       // strips x (out_end - out_begin) row steps
     long long bounds[kMaxWorkers + 1];   // pipeline w walks row steps [bounds[w], bounds[w+1]) of the strip-major order (tc2_partition)
@@ -512,6 +513,22 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
                 rows_done++;
                 if (warp0 && leader) ctr_publish(ctr + 16, rows_done);   // conv1 of rows_done rows complete: their oldest ring rows may go
                 TL2(0, i, 1);
+                if (p.e1_wide) {
+                    // two 32-column loads: a tcgen05.ld round trip costs ~160 cycles whatever its width, and E1 sits on the
+                    // unit's critical path (conv1 -> E1 -> conv2 -> E2 -> conv3 -> E3 -> unit free again): two round trips
+                    // instead of four
+                    uint32_t v[32], w[32];
+                    tmem_ld32(un, v);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int c = 0; c < 16; c++) v[c] = relu_pack_f16x2(__uint_as_float(v[2 * c]), __uint_as_float(v[2 * c + 1]));
+                    tmem_ld32(un + 32, w);
+                    tmem_st16(un, v);          // columns 0..15 were read by the first load (complete)
+                    tc_wait_ld();
+#pragma unroll
+                    for (int c = 0; c < 16; c++) w[c] = relu_pack_f16x2(__uint_as_float(w[2 * c]), __uint_as_float(w[2 * c + 1]));
+                    tmem_st16(un + 16, w);
+                } else {
                 // four 16-column chunks, software-pipelined: chunk k+1 is in flight while chunk k is packed
                 uint32_t va[16], vb[16], r[8];
                 tmem_ld16(un, va);
@@ -534,6 +551,7 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
 #pragma unroll
                 for (int c = 0; c < 8; c++) r[c] = relu_pack_f16x2(__uint_as_float(vb[2 * c]), __uint_as_float(vb[2 * c + 1]));
                 tmem_st8(un + 24, r);
+                }
                 tc_wait_st();
                 tc_fence_before();
                 TL2(0, i, 2);
@@ -925,6 +943,7 @@ int launch_cnn_tc2(Ctx* c, const CnnArgs& a) {
     p.cr = a.cr; p.cb = a.cb;
     p.bgr = a.bgr; p.bgr_stride = a.bgr_stride;
     p.swap_rb = a.order == SRCNN_ORDER_RGB ? 1 : 0;
+    p.e1_wide = c->tc2_e1_wide;
     p.wimg = (const uint8_t*)c->d_tc2_weights;
     const int nstrips = (a.W + kStripCols - 1) / kStripCols;
     p.total = (long long)nstrips * (a.out_end - a.out_begin);
