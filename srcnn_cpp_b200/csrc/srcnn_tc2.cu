@@ -178,8 +178,25 @@ __device__ __forceinline__ void ctr_wait_ge4(uint32_t addr, uint32_t need, int* 
 // A warpgroup waits for a tcgen05.commit: ONE warp polls the mbarrier, the other three park in a hardware named barrier
 // (no issue slots).  A parked try_wait returns every ~50 cycles; with all four warps of three roles polling, the polls
 // were 38 % of all executed instructions.
-__device__ __forceinline__ void wg_wait(uint32_t bar, uint32_t parity, bool poller, int barid, int* guard, int code) {
+__device__ __forceinline__ uint32_t mbar_test_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+__device__ __forceinline__ void wg_wait(uint32_t bar, uint32_t parity, bool poller, int barid, int* guard, int code, int spin = 0) {
     if (poller) {
+        if (spin) {   // non-blocking test in a tight loop (A/B knob SRCNN_TC2_SPIN): one warp per warpgroup spins
+            uint32_t tries = 0;
+            while (!mbar_test_wait(bar, parity)) {
+                if (++tries > (1u << 26)) { *guard = code; __threadfence_system(); __trap(); }
+            }
+        } else
         mbar_wait(bar, parity, guard, code);
         tc_fence_after();
         tc_fence_before();
@@ -296,6 +313,7 @@ struct Params {
     uint8_t* bgr;          // interleaved result, row out_begin first
     size_t bgr_stride;
     int swap_rb;           // 1: R,G,B byte order
+    int spin;              // completion barriers are polled with test_wait instead of try_wait (A/B knob)
     int e1_wide;           // E1 reads D1 with two 32-column loads (default) instead of four 16-column ones
     const uint8_t* wimg;   // packed FP16 operand image (kWeightBytes)
     long long total;       // strips x (out_end - out_begin) row steps
@@ -364,7 +382,7 @@ __device__ __forceinline__ void e3_step(const E3Ctx& c, const uint32_t (&hx_r)[5
     uint32_t tv[25];   // the 25 taps: three loads (16 + 8 + 1 columns) instead of one 32-register block
     TL2(2, rho - c.ta, 0);
     if (has_t) {
-        wg_wait(c.bars + 48 + uc.u * 8, uc.par, c.poller, 10 + pipe, p.guard, 40);   // TFULL
+        wg_wait(c.bars + 48 + uc.u * 8, uc.par, c.poller, 10 + pipe, p.guard, 40, p.spin);   // TFULL
         const uint32_t t = c.tml + uc.u * kUnitCols;
         tmem_ld16(t, tv);     // in flight while the previous row is stored
         tmem_ld8(t + 16, tv + 16);
@@ -509,7 +527,7 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
             for (int i = 0; i < nT; i++) {
                 const uint32_t un = tml + uc.u * kUnitCols;
                 TL2(0, i, 0);
-                wg_wait(D1FULL(uc.u), uc.par, warp0, 3 + pipe, p.guard, 20);
+                wg_wait(D1FULL(uc.u), uc.par, warp0, 3 + pipe, p.guard, 20, p.spin);
                 rows_done++;
                 if (warp0 && leader) ctr_publish(ctr + 16, rows_done);   // conv1 of rows_done rows complete: their oldest ring rows may go
                 TL2(0, i, 1);
@@ -576,7 +594,7 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
             for (int i = 0; i < nT; i++) {
                 const uint32_t un = tml + uc.u * kUnitCols;
                 TL2(3, i, 0);
-                wg_wait(D2FULL(uc.u), uc.par, warp0, 5 + pipe, p.guard, 21);
+                wg_wait(D2FULL(uc.u), uc.par, warp0, 5 + pipe, p.guard, 21, p.spin);
                 TL2(3, i, 1);
                 uint32_t va[32];
                 tmem_ld32(un + 32, va);
@@ -944,6 +962,7 @@ int launch_cnn_tc2(Ctx* c, const CnnArgs& a) {
     p.bgr = a.bgr; p.bgr_stride = a.bgr_stride;
     p.swap_rb = a.order == SRCNN_ORDER_RGB ? 1 : 0;
     p.e1_wide = c->tc2_e1_wide;
+    p.spin = c->tc2_spin;
     p.wimg = (const uint8_t*)c->d_tc2_weights;
     const int nstrips = (a.W + kStripCols - 1) / kStripCols;
     p.total = (long long)nstrips * (a.out_end - a.out_begin);
