@@ -178,25 +178,8 @@ __device__ __forceinline__ void ctr_wait_ge4(uint32_t addr, uint32_t need, int* 
 // A warpgroup waits for a tcgen05.commit: ONE warp polls the mbarrier, the other three park in a hardware named barrier
 // (no issue slots).  A parked try_wait returns every ~50 cycles; with all four warps of three roles polling, the polls
 // were 38 % of all executed instructions.
-__device__ __forceinline__ uint32_t mbar_test_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok;
-}
-__device__ __forceinline__ void wg_wait(uint32_t bar, uint32_t parity, bool poller, int barid, int* guard, int code, int spin = 0) {
+__device__ __forceinline__ void wg_wait(uint32_t bar, uint32_t parity, bool poller, int barid, int* guard, int code) {
     if (poller) {
-        if (spin) {   // non-blocking test in a tight loop (A/B knob SRCNN_TC2_SPIN): one warp per warpgroup spins
-            uint32_t tries = 0;
-            while (!mbar_test_wait(bar, parity)) {
-                if (++tries > (1u << 26)) { *guard = code; __threadfence_system(); __trap(); }
-            }
-        } else
         mbar_wait(bar, parity, guard, code);
         tc_fence_after();
         tc_fence_before();
@@ -313,7 +296,9 @@ struct Params {
     uint8_t* bgr;          // interleaved result, row out_begin first
     size_t bgr_stride;
     int swap_rb;           // 1: R,G,B byte order
-    int spin;              // completion barriers are polled with test_wait instead of try_wait (A/B knob)
+    int prod_rot;          // ring producer as four independent warps that take the conv1 issue in turn (default) or the lock-step form
+    int whatif;            // profiling aid (SRCNN_TC2_WHATIF, results become garbage): bit 0 conv1 issues one MMA, 1 E3 skips sums/exchange/store,
+                           // 2 E1 skips load/pack/store, 3 producer skips gather + ring store, 4 E2 skips load/pack/store, 5 conv2/conv3 issue one MMA
     int e1_wide;           // E1 reads D1 with two 32-column loads (default) instead of four 16-column ones
     const uint8_t* wimg;   // packed FP16 operand image (kWeightBytes)
     long long total;       // strips x (out_end - out_begin) row steps
@@ -326,6 +311,15 @@ constexpr int kDbgRows = 64, kDbgSlots = 8;
     do {                                                                                                          \
         if constexpr (DBG)                                                                                        \
             if (blockIdx.x == 0 && pipe == 0 && tp == 0 && first_seg &&  \
+                (row_) >= 0 && (row_) < kDbgRows)                                                                 \
+                p.dbg[(((role_) * kDbgRows) + (row_)) * kDbgSlots + (slot_)] = clock64();                        \
+    } while (0)
+
+// same, stamped by lane 0 of the role's MMA-issuing warp (warp 2 of the warpgroup in pipeline 0)
+#define TL2W(role_, row_, slot_)                                                                                  \
+    do {                                                                                                          \
+        if constexpr (DBG)                                                                                        \
+            if (blockIdx.x == 0 && pipe == 0 && tp == 64 && first_seg &&  \
                 (row_) >= 0 && (row_) < kDbgRows)                                                                 \
                 p.dbg[(((role_) * kDbgRows) + (row_)) * kDbgSlots + (slot_)] = clock64();                        \
     } while (0)
@@ -382,7 +376,8 @@ __device__ __forceinline__ void e3_step(const E3Ctx& c, const uint32_t (&hx_r)[5
     uint32_t tv[25];   // the 25 taps: three loads (16 + 8 + 1 columns) instead of one 32-register block
     TL2(2, rho - c.ta, 0);
     if (has_t) {
-        wg_wait(c.bars + 48 + uc.u * 8, uc.par, c.poller, 10 + pipe, p.guard, 40, p.spin);   // TFULL
+        wg_wait(c.bars + 48 + uc.u * 8, uc.par, c.poller, 10 + pipe, p.guard, 40);   // TFULL
+        TL2(2, rho - c.ta, 1);
         const uint32_t t = c.tml + uc.u * kUnitCols;
         tmem_ld16(t, tv);     // in flight while the previous row is stored
         tmem_ld8(t + 16, tv + 16);
@@ -394,6 +389,7 @@ __device__ __forceinline__ void e3_step(const E3Ctx& c, const uint32_t (&hx_r)[5
         __syncwarp();
         nfreed++;
         if (c.leader) ctr_publish(c.freed, nfreed);            // the unit may be overwritten by conv1 of row +3
+        TL2(2, rho - c.ta, 2);
         uc.next();
             // T[m*5+n] belongs to output row rho - (m-2): window position k = 4 - m
 #pragma unroll
@@ -416,7 +412,7 @@ __device__ __forceinline__ void e3_step(const E3Ctx& c, const uint32_t (&hx_r)[5
         }
     }
     const int r = rho - 2;
-    if (r >= c.ra && r < c.rb) {       // output row r is complete: publish its five horizontal-tap partial sums
+    if (r >= c.ra && r < c.rb && !(p.whatif & 2)) {       // output row r is complete: publish its five horizontal-tap partial sums
         uint32_t vcr = 128u, vcb = 128u;
         if (FUSED && c.col_ok) {       // chroma of this pixel: in flight across the exchange
             vcr = *crp;
@@ -427,6 +423,7 @@ __device__ __forceinline__ void e3_step(const E3Ctx& c, const uint32_t (&hx_r)[5
 #pragma unroll
         for (int n = 0; n < 5; n++) st_shared_f32(c.hx_w + bo + n * 512, acc[PH % 5][n]);
         named_bar(10 + pipe, 128);
+        TL2(2, rho - c.ta, 3);
         float v[5];
 #pragma unroll
         for (int n = 0; n < 5; n++) v[n] = ld_shared_f32(hx_r[n] + bo);
@@ -505,7 +502,7 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
     // landing on sub-partition 0.
     const bool warp0 = (tp >> 5) == ((ROLE == 1 ? 0 : 2) + pipe);
     const uint32_t leader = elect_one();
-    if (ROLE != 2 && warp0) mbar_wait(wbar, 0, p.guard, 1);   // packed operands have landed in shared memory
+    if (ROLE != 2 && (warp0 || (ROLE == 1 && p.prod_rot))) mbar_wait(wbar, 0, p.guard, 1);   // packed operands have landed in shared memory
 
     while (lin < lin_end) {
         // ---- one segment: strip `strip`, output rows [ra, rb) ----
@@ -527,11 +524,12 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
             for (int i = 0; i < nT; i++) {
                 const uint32_t un = tml + uc.u * kUnitCols;
                 TL2(0, i, 0);
-                wg_wait(D1FULL(uc.u), uc.par, warp0, 3 + pipe, p.guard, 20, p.spin);
+                wg_wait(D1FULL(uc.u), uc.par, warp0, 3 + pipe, p.guard, 20);
                 rows_done++;
                 if (warp0 && leader) ctr_publish(ctr + 16, rows_done);   // conv1 of rows_done rows complete: their oldest ring rows may go
                 TL2(0, i, 1);
-                if (p.e1_wide) {
+                if (p.whatif & 4) {
+                } else if (p.e1_wide) {
                     // two 32-column loads: a tcgen05.ld round trip costs ~160 cycles whatever its width, and E1 sits on the
                     // unit's critical path (conv1 -> E1 -> conv2 -> E2 -> conv3 -> E3 -> unit free again): two round trips
                     // instead of four
@@ -576,16 +574,19 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
                 named_bar(3 + pipe, 128);   // A1 complete in all 128 lanes
                 if (warp0) {   // conv2(i): D2 = A1 x W2 + b2 (the ones column of the ring carries the bias)
                     tc_fence_after();
-                    TL2(0, i, 3);
+                    TL2W(0, i, 3);
                     if (leader) {
                         const uint32_t ut = tm + uc.u * kUnitCols;
 #pragma unroll
-                        for (int ks = 0; ks < 4; ks++)
+                        for (int ks = 0; ks < 4; ks++) {
+                            if ((p.whatif & 32) && ks > 0) break;
                             mma_ts2(ut + 32, ut + ks * 8, b2lo + ks * 64, desc_hi(128), idesc_f16(32), ks > 0);
-                        mma_ts2(ut + 32, ring + 48, b2lo + 4 * 64, desc_hi(128), idesc_f16(32), 1);
+                        }
+                        if (!(p.whatif & 32)) mma_ts2(ut + 32, ring + 48, b2lo + 4 * 64, desc_hi(128), idesc_f16(32), 1);
                         mma_commit(D2FULL(uc.u));
                     }
                     __syncwarp();
+                    TL2W(0, i, 4);
                 }
                 uc.next();
             }
@@ -594,34 +595,135 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
             for (int i = 0; i < nT; i++) {
                 const uint32_t un = tml + uc.u * kUnitCols;
                 TL2(3, i, 0);
-                wg_wait(D2FULL(uc.u), uc.par, warp0, 5 + pipe, p.guard, 21, p.spin);
+                wg_wait(D2FULL(uc.u), uc.par, warp0, 5 + pipe, p.guard, 21);
                 TL2(3, i, 1);
-                uint32_t va[32];
-                tmem_ld32(un + 32, va);
-                tc_wait_ld();
+                if (!(p.whatif & 16)) {
+                    uint32_t va[32];
+                    tmem_ld32(un + 32, va);
+                    tc_wait_ld();
 #pragma unroll
-                for (int c = 0; c < 16; c++) va[c] = relu_pack_f16x2(__uint_as_float(va[2 * c]), __uint_as_float(va[2 * c + 1]));
-                tmem_st16(un + 32, va);
+                    for (int c = 0; c < 16; c++) va[c] = relu_pack_f16x2(__uint_as_float(va[2 * c]), __uint_as_float(va[2 * c + 1]));
+                    tmem_st16(un + 32, va);
+                }
                 tc_wait_st();
                 tc_fence_before();
                 TL2(3, i, 2);
                 named_bar(5 + pipe, 128);   // A2 complete in all 128 lanes
                 if (warp0) {   // conv3(i) tap GEMM: T = A2 x W3
                     tc_fence_after();
-                    TL2(3, i, 3);
+                    TL2W(3, i, 3);
                     if (leader) {
                         const uint32_t ut = tm + uc.u * kUnitCols;
 #pragma unroll
-                        for (int ks = 0; ks < 2; ks++)
+                        for (int ks = 0; ks < 2; ks++) {
+                            if ((p.whatif & 32) && ks > 0) break;
                             mma_ts2(ut, ut + 32 + ks * 8, b3lo + ks * 64, desc_hi(128), idesc_f16(32), ks > 0);
+                        }
                         mma_commit(TFULL(uc.u));
                     }
                     __syncwarp();
+                    TL2W(3, i, 4);
                 }
                 uc.next();
             }
         } else if constexpr (ROLE == 1) {
             // ================= im2col ring producer =================
+            if (p.prod_rot) {
+                // Four INDEPENDENT warps: each stages the 40 tile columns its own 32 lanes need (private shared-memory rows, warp-level
+                // sync only), writes its lanes' ring slot, and takes every fourth row's conv1 issue.  The only cross-warp hand-off is
+                // "ring row t is written in all 128 lanes": the three other warps ARRIVE on a named barrier and run on, the row's
+                // issuing warp SYNCs on it.  The serial chain per row (stage, gather, TMEM store + wait, issue of seven MMAs at the
+                // tensor-pipe rate, bookkeeping) was ~850 cycles in one warp with its three siblings waiting for it at a full
+                // barrier every row; spread like this the issue costs each warp a quarter of a row's issue time.
+                const int myq = tp >> 5, lane = tp & 31;
+                const uint32_t ybuf = sbase + kOffY + pipe * (kYSlots * kYRowBytes) + myq * 192;   // two private rows of 48 FP16
+                const int xc0 = min(max(xs - 6 + 32 * myq + lane, 0), W - 1);                 // tile column 32*myq + lane
+                const int xc1 = min(max(xs - 6 + 32 * myq + 32 + (lane & 7), 0), W - 1);      // tile columns 32*myq + 32..39
+                auto plane_row = [&](int q) { return min(max(min(max(ta - 4 + q, 0), H - 1) - p.row0, 0), p.rows - 1); };
+                int prow = plane_row(0);
+                const uint8_t* yp0 = p.y + (size_t)prow * p.pitch + xc0;
+                const uint8_t* yp1 = p.y + (size_t)prow * p.pitch + xc1;
+                const size_t ypitch = p.pitch;
+                auto fetch = [&](int q, uint32_t& v0, uint32_t& v1) {   // must be called with q = 0, 1, 2, ... in order
+                    const int r = plane_row(q);
+                    if (r != prow) { yp0 += ypitch; yp1 += ypitch; prow = r; }
+                    v0 = *yp0;
+                    v1 = *yp1;
+                };
+                const uint32_t st_my = ybuf + lane * 2, st_x = ybuf + (32 + (lane & 7)) * 2;
+                auto stage = [&](int q, uint32_t v0, uint32_t v1) {   // exact u8 -> FP16
+                    const uint32_t ro = (q & 1) * 96;
+                    st_shared_u16(st_my + ro, __half_as_ushort(__ushort2half_rn((unsigned short)v0)));
+                    st_shared_u16(st_x + ro, __half_as_ushort(__ushort2half_rn((unsigned short)v1)));
+                };
+                uint32_t slot = slot0, rot = slot0, seen_c = 0u;
+                const uint32_t gbase = rows_done;
+                const uint32_t gaddr = ybuf + ((lane >> 1) << 2);
+                const uint32_t sh = (lane & 1) * 16;
+                uint32_t a0 = 0, a1 = 0;
+                fetch(0, a0, a1);
+                stage(0, a0, a1);
+                if (nP > 1) fetch(1, a0, a1);
+                __syncwarp();
+                for (int t = 0; t < nP; t++) {
+                    TL2(1, t, 0);
+                    uint32_t w[6], o[5];
+                    const uint32_t rowaddr = gaddr + (t & 1) * 96;
+#pragma unroll
+                    for (int k = 0; k < 6; k++) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w[k]) : "r"(rowaddr + 4 * k));
+#pragma unroll
+                    for (int k = 0; k < 5; k++) o[k] = __funnelshift_r(w[k], w[k + 1], sh);
+                    o[4] &= 0xFFFFu;
+                    TL2(1, t, 1);
+                    if (t >= kSlots) {   // ring row t reuses the slot of row t-11, last read by conv1 of that row
+                        const uint32_t need = gbase + (uint32_t)(t + 1 - kSlots);
+                        if ((int)(seen_c - need) < 0) ctr_wait_ge(ctr + 16, need, p.guard, 30);
+                    }
+                    TL2(1, t, 2);
+                    const uint32_t sl = tml + kRingOff + slot * kSlotCols;
+                    if (!(p.whatif & 8)) {
+                        tmem_st4(sl, o[0], o[1], o[2], o[3]);
+                        tmem_st1(sl + 4, o[4]);
+                    }
+                    if (t + 1 < nP) stage(t + 1, a0, a1);
+                    if (t + 2 < nP) fetch(t + 2, a0, a1);
+                    tc_wait_st();
+                    tc_fence_before();
+                    TL2(1, t, 3);
+                    if (t >= 8) {   // conv1 of row t-8: its last ring row is being completed
+                        // a warp may run two rows ahead of a pending issue (writing row t needs conv1 of step t-3 complete, no more):
+                        // three barrier ids in turn, so that an arrival for row t can never land on the barrier of row t-2 or t-1
+                        const int tm3 = t % 3;
+                        const int bid = (tm3 == 0 ? 1 : (tm3 == 1 ? 12 : 14)) + pipe;
+                        if (((t + pipe) & 3) == myq) {
+                            named_bar(bid, 128);
+                            TL2(1, t, 5);
+                            if (rows_done >= 3u) ctr_wait_ge4(ctr, rows_done - 2u, p.guard, 11);   // E3 has read T of row g-3: unit free
+                            tc_fence_after();
+                            TL2(1, t, 6);
+                            if (leader) {
+                                const uint32_t d = tm + uc.u * kUnitCols;
+                                const uint32_t b = b1lo + rot * (kB1Var >> 4);
+#pragma unroll
+                                for (int ch = 0; ch < kC1Chunks; ch++) {
+                                    if ((p.whatif & 1) && ch > 0) break;
+                                    mma_ts2(d, ring + ch * 8, b + ch * (kB1Chunk >> 4), desc_hi(128), idesc_f16(64), ch > 0);
+                                }
+                                mma_commit(D1FULL(uc.u));
+                            }
+                            TL2(1, t, 7);
+                        } else {
+                            asm volatile("bar.arrive %0, %1;" ::"r"(bid), "r"(128) : "memory");
+                        }
+                        uc.next();
+                        rows_done++;
+                        if (++rot == (uint32_t)kSlots) rot = 0;
+                    }
+                    __syncwarp();   // the row staged above is read by the other lanes of this warp in the next step
+                    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(seen_c) : "r"(ctr + 16) : "memory");
+                    if (++slot == (uint32_t)kSlots) slot = 0;
+                }
+            } else {
             const int ybar = 1 + pipe;
             const uint32_t yst_s = sbase + kOffY + pipe * (kYSlots * kYRowBytes);
             // Staging the next Y row (global load, u8 -> FP16, shared store) is left to the three warps that do NOT issue conv1:
@@ -674,8 +776,10 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
                 o[4] &= 0xFFFFu;
                 TL2(1, t, 1);
                 const uint32_t sl = tml + kRingOff + slot * kSlotCols;
-                tmem_st4(sl, o[0], o[1], o[2], o[3]);
-                tmem_st1(sl + 4, o[4]);
+                if (!(p.whatif & 8)) {
+                    tmem_st4(sl, o[0], o[1], o[2], o[3]);
+                    tmem_st1(sl + 4, o[4]);
+                }
                 if (t + 1 < nP) stage(t + 1, nxt0, nxt1);   // loaded one full step ago
                 if (t + 2 < nP) fetch(t + 2, nxt0, nxt1);   // issued AFTER the use above: the scoreboard the conversion waits on
                                                             // must not also count a load that has just been issued
@@ -703,8 +807,10 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
                         const uint32_t d = tm + uc.u * kUnitCols;
                         const uint32_t b = b1lo + rot * (kB1Var >> 4);
 #pragma unroll
-                        for (int ch = 0; ch < kC1Chunks; ch++)
+                        for (int ch = 0; ch < kC1Chunks; ch++) {
+                            if ((p.whatif & 1) && ch > 0) break;
                             mma_ts2(d, ring + ch * 8, b + ch * (kB1Chunk >> 4), desc_hi(128), idesc_f16(64), ch > 0);
+                        }
                         mma_commit(D1FULL(uc.u));
                     }
                     __syncwarp();
@@ -726,6 +832,7 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
             if (nP > 1) fetch(1, a0, a1);
             named_bar(ybar, 128);   // row 0 staged
             for (int t = 0; t < nP; t++) step(t, a0, a1);
+            }
         } else {
             // ================= E3: conv3 tap sums =================
             const uint32_t hx_s = sbase + kOffHx + pipe * kHxBytes;
@@ -962,7 +1069,8 @@ int launch_cnn_tc2(Ctx* c, const CnnArgs& a) {
     p.bgr = a.bgr; p.bgr_stride = a.bgr_stride;
     p.swap_rb = a.order == SRCNN_ORDER_RGB ? 1 : 0;
     p.e1_wide = c->tc2_e1_wide;
-    p.spin = c->tc2_spin;
+    p.whatif = c->tc2_whatif;
+    p.prod_rot = c->tc2_prod_rot;
     p.wimg = (const uint8_t*)c->d_tc2_weights;
     const int nstrips = (a.W + kStripCols - 1) / kStripCols;
     p.total = (long long)nstrips * (a.out_end - a.out_begin);

@@ -13,17 +13,10 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
-CONFIGS = [
-    ("base(ovh0,e1n,try)", dict(SRCNN_TC2_SEG_OVH="0", SRCNN_TC2_E1_WIDE="0", SRCNN_TC2_SPIN="0")),
-    ("ovh8", dict(SRCNN_TC2_SEG_OVH="8", SRCNN_TC2_E1_WIDE="0", SRCNN_TC2_SPIN="0")),
-    ("ovh12", dict(SRCNN_TC2_SEG_OVH="12", SRCNN_TC2_E1_WIDE="0", SRCNN_TC2_SPIN="0")),
-    ("ovh16", dict(SRCNN_TC2_SEG_OVH="16", SRCNN_TC2_E1_WIDE="0", SRCNN_TC2_SPIN="0")),
-    ("ovh20", dict(SRCNN_TC2_SEG_OVH="20", SRCNN_TC2_E1_WIDE="0", SRCNN_TC2_SPIN="0")),
-    ("ovh12+e1wide", dict(SRCNN_TC2_SEG_OVH="12", SRCNN_TC2_E1_WIDE="1", SRCNN_TC2_SPIN="0")),
-    ("ovh12+spin", dict(SRCNN_TC2_SEG_OVH="12", SRCNN_TC2_E1_WIDE="0", SRCNN_TC2_SPIN="1")),
-    ("ovh12+e1wide+spin", dict(SRCNN_TC2_SEG_OVH="12", SRCNN_TC2_E1_WIDE="1", SRCNN_TC2_SPIN="1")),
-    ("ovh16+e1wide", dict(SRCNN_TC2_SEG_OVH="16", SRCNN_TC2_E1_WIDE="1", SRCNN_TC2_SPIN="0")),
-]
+CONFIGS = [(n, dict(SRCNN_TC2_PROD_ROT=str(r), SRCNN_TC2_WHATIF=str(v))) for n, r, v in [
+    ("lockstep", 0, 0), ("rot", 1, 0), ("lockstep skeleton", 0, 63), ("rot skeleton", 1, 63), ("rot conv1=1mma", 1, 1),
+    ("rot E3 no out", 1, 2), ("rot E1 no work", 1, 4), ("rot E2 no work", 1, 16), ("rot no epilogue work", 1, 22)]]
+CHECK_BYTES = True   # among the settings that leave the arithmetic on (WHATIF=0)
 
 
 def main():
@@ -60,8 +53,9 @@ def main():
         torch.cuda.synchronize()
         ms = np.array([a.elapsed_time(b) for a, b in ts])
         got = outs[0].cpu().numpy()
-        same = True if ref_bytes is None else bool(np.array_equal(ref_bytes, got))
-        if ref_bytes is None:
+        full = env.get("SRCNN_TC2_WHATIF", "0") == "0"
+        same = True if (ref_bytes is None or not full) else bool(np.array_equal(ref_bytes, got))
+        if ref_bytes is None and full:
             ref_bytes = got.copy()
         # colour + bicubic alone
         for i in range(3):
@@ -83,7 +77,7 @@ def main():
                    colour_ms_median=float(np.median(msa)), same_bytes=same)
         rows.append(row)
         print(json.dumps(row), flush=True)
-    assert all(r["same_bytes"] for r in rows), "a tuning knob changed the results"
+    assert not CHECK_BYTES or all(r["same_bytes"] for r in rows), "a tuning knob changed the results"
 
 
 if __name__ == "__main__":

@@ -24,16 +24,17 @@ for i in range(lo, hi):
 print("E1 (row i): D1full wait | work + arrive | wait all arrived | issue conv2")
 for i in range(lo, hi):
     r = a[0, i]
-    print(" i%2d  t=%7d  wait %5d  work %5d  allwait %5d   period %5d" % (i, r[0] - t0, r[1] - r[0], r[2] - r[1], r[3] - r[2], a[0, i + 1, 0] - r[0]))
+    print(" i%2d  t=%7d  wait %5d  work %5d  allwait %5d  issue %5d   period %5d" % (i, r[0] - t0, r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] - r[3], a[0, i + 1, 0] - r[0]))
 print("E2 (row i): D2full wait | work + arrive | wait all arrived | issue conv3")
 for i in range(lo, hi):
     r = a[3, i]
-    print(" i%2d  t=%7d  wait %5d  work %5d  allwait %5d   period %5d" % (i, r[0] - t0, r[1] - r[0], r[2] - r[1], r[3] - r[2], a[3, i + 1, 0] - r[0]))
-print("E3 (row): whole step (T wait + load, 25 tap adds, exchange, store)")
+    print(" i%2d  t=%7d  wait %5d  work %5d  allwait %5d  issue %5d   period %5d" % (i, r[0] - t0, r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] - r[3], a[3, i + 1, 0] - r[0]))
+print("E3 (row): Tfull wait | T load + freed | tap adds + publish + bar (row-2) | exchange read, store")
 for i in range(lo, hi):
     r = a[2, i]
-    print(" i%2d  t=%7d  step %5d   period %5d" % (i, r[0] - t0, r[4] - r[0], a[2, i + 1, 0] - r[0]))
+    print(" i%2d  t=%7d  wait %5d  load %5d  adds+bar %5d  out %5d   step %5d   period %5d" % (
+        i, r[0] - t0, r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] - r[3], r[4] - r[0], a[2, i + 1, 0] - r[0]))
 i = 34
-ev = [("conv1 issue", a[1, i + 8, 6]), ("D1full seen", a[0, i, 1]), ("A1ready", a[0, i, 2]), ("conv2 issue", a[0, i, 3]),
-      ("D2 seen", a[3, i, 1]), ("A2ready", a[3, i, 2]), ("conv3 issue", a[3, i, 3]), ("E3 step done", a[2, i, 4])]
+ev = [("conv1 issue", a[1, i + 8, 6]), ("conv1 issued", a[1, i + 8, 7]), ("D1full seen", a[0, i, 1]), ("A1ready", a[0, i, 2]), ("conv2 issue", a[0, i, 3]), ("conv2 issued", a[0, i, 4]),
+      ("D2 seen", a[3, i, 1]), ("A2ready", a[3, i, 2]), ("conv3 issue", a[3, i, 3]), ("conv3 issued", a[3, i, 4]), ("T seen", a[2, i, 1]), ("T loaded, unit freed", a[2, i, 2]), ("E3 step done", a[2, i, 4])]
 print("row %d life: " % i + "  ".join("%s +%d" % (n, v - ev[0][1]) for n, v in ev))
