@@ -55,10 +55,11 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("SRCNN_B200_LIB", LIB_PATH)   # override: A/B runs of two builds of the library (tools/ab_libs.sh)
+    if not os.path.exists(path):
         raise FileNotFoundError(
-            LIB_PATH + " is missing: run `make` (or __graft_entry__.build()). There is no CPU fallback.")
-    L = C.CDLL(LIB_PATH)
+            path + " is missing: run `make` (or __graft_entry__.build()). There is no CPU fallback.")
+    L = C.CDLL(path)
     vp, u8p, i32p, sz = C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.c_size_t
     L.srcnn_abi_version.restype = C.c_int
     L.srcnn_strerror.restype = C.c_char_p

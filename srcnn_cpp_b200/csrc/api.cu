@@ -228,9 +228,6 @@ int srcnn_create(srcnn_ctx** out, int device, int variant) {
     if (rc) return bail(rc);
     if (const char* k = getenv("SRCNN_TC_KERNEL")) c->tc_kernel = atoi(k) == 1 ? 1 : 2;
     if (const char* k = getenv("SRCNN_FUSE_MERGE")) c->fuse_merge = atoi(k) != 0;
-    if (const char* k = getenv("SRCNN_TC2_E1_WIDE")) c->tc2_e1_wide = atoi(k) != 0;   // tuning aid
-    if (const char* k = getenv("SRCNN_TC2_PROD_ROT")) c->tc2_prod_rot = atoi(k) != 0;   // tuning aid
-    if (const char* k = getenv("SRCNN_TC2_WHATIF")) c->tc2_whatif = atoi(k);   // profiling aid: results become garbage
     if (const char* k = getenv("SRCNN_TC2_SEG_OVH")) c->tc2_seg_ovh = std::max(0, std::min(64, atoi(k)));   // tuning aid
     *out = c;
     return SRCNN_OK;

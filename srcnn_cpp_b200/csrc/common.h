@@ -80,9 +80,6 @@ struct Ctx {
                                      // (SRCNN_FUSE_MERGE=1; byte-identical, but 0.236 vs 0.214 ms per 4K frame: off by default)
     Tc2Partition tc2_part;
     int tc2_seg_ovh = 12;            // cost of opening a segment, in row steps (SRCNN_TC2_SEG_OVH; 0 = cut into equal row counts)
-    int tc2_e1_wide = 1;             // E1 epilogue: two 32-column TMEM loads per row (1) or four 16-column ones (0; SRCNN_TC2_E1_WIDE)
-    int tc2_prod_rot = 1;            // ring producer: independent warps with rotating conv1 issue (1) or lock-step (0; SRCNN_TC2_PROD_ROT)
-    int tc2_whatif = 0;              // profiling aid: stages of the row-walking kernel switched off to see what bounds it (SRCNN_TC2_WHATIF)
     int tc_kernel = 2;               // 2 = row-walking kernel (default), 1 = first-generation kernel (SRCNN_TC_KERNEL=1)
     int* d_guard = nullptr;          // device-side watchdog flag (mapped pinned)
     int* h_guard = nullptr;
