@@ -276,7 +276,7 @@ def run_ours(args, rank, world, local_rank):
                          "achieved": achieved, "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16"],
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture of this
                          # command (profiles/r1_summary.md); the Y' plane it writes stays in L2 for the merge kernel
-                         "traffic": (8.49e6 if args.variant != "fp32" else None),
+                         "traffic": (8.51e6 if args.variant != "fp32" else None),
                          "peak_source": peaks["src"], "kernel_ms": k_ms,
                          "algorithmic_flop_per_launch": FLOP_PER_PX * px_step},
             "stages": {"colour_bicubic_ms": a_ms / max(1, calls), "srcnn_ms": k_ms, "merge_ms": c_ms / max(1, calls),
