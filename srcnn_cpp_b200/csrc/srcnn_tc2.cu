@@ -478,7 +478,7 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
     (void)first_seg;
 
     // barrier cursors run on across segments (every row / ring row arrives exactly once on its barrier)
-    UnitCursor uc, uc2;              // uc: this role's main row cursor; uc2: second stage of the role (E2 / conv3 / ring-free)
+    UnitCursor uc;                   // this role's row cursor over the pipeline's three units
     uint32_t rows_done = 0;          // conv1 issuer: rows issued so far (the first three find their unit free)
     uint32_t npub = 0;               // E3: rows published to the horizontal exchange so far
     (void)rows_done; (void)npub;
@@ -602,7 +602,6 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
             // the issuing warp's serial chain is the pipeline's bottleneck.  96 lanes cover the 136 tile columns: s and
             // 96 + s mod 40 (lanes 40.. repeat a column: same value, no divergence).
             const int myq = tp >> 5, issq = pipe;                            // this warp's quarter, the issuing quarter
-            const bool chk = myq == ((issq + 1) & 3);                        // the warp that watches the progress counters
             const int sidx = (myq - (myq > issq ? 1 : 0)) * 32 + (tp & 31);  // 0..95 over the staging lanes
             const int sj1 = 96 + sidx % 40;
             const int xc0 = min(max(xs - 6 + sidx, 0), W - 1);               // tile column sidx
