@@ -226,30 +226,20 @@ __global__ void __launch_bounds__(256) k_color_bicubic_tiled(ResizeDev p) {
     const int nsc = sx_hi - sx_lo + 1, nsr = sy_hi - sy_lo + 1;
     const int tid = threadIdx.x;
 
-    // (1) colour-convert the footprint (replicate border applied here).  A thread keeps ONE footprint column and walks down
-    //     the rows (256 / cw rows per pass, cw = the footprint width rounded up to 8): the column clamp, the byte offset in
-    //     the source row and the shared-memory column are computed once per thread, not once per pixel (a flat index over
-    //     the footprint cost 65 instructions per source pixel, most of them index arithmetic; this form costs ~30)
-    {
-        const int cw = (nsc + 7) & ~7;
-        const int rp = 256 / cw;                                   // >= 3 (cw <= 80)
-        const int tr = (int)(((unsigned)tid * (((1u << 16) + (unsigned)cw - 1u) / (unsigned)cw)) >> 16);   // tid / cw, exact for tid < 256
-        const int tc = tid - tr * cw;
-        if (tr < rp && tc < nsc) {
-            const size_t xoff = 3 * (size_t)clampi(sx_lo + tc, 0, p.sw - 1);
-#pragma unroll 2
-            for (int r = tr; r < nsr; r += rp) {
-                const int gy = clampi(sy_lo + r, 0, p.sh - 1) - p.src_row0;
-                const uint8_t* px = p.src + (size_t)gy * p.src_stride + xoff;
-                const int c0 = px[0], c1 = px[1], c2 = px[2];
-                const int B = p.swapRB ? c2 : c0, R = p.swapRB ? c0 : c2;
-                int Y, Cr, Cb;
-                bgr_to_ycc(B, c1, R, Y, Cr, Cb);
-                sP[0][r][tc] = (uint8_t)Y;
-                sP[1][r][tc] = (uint8_t)Cr;
-                sP[2][r][tc] = (uint8_t)Cb;
-            }
-        }
+    // (1) colour-convert the footprint (replicate border applied here); i / nsc by multiply-shift (exact for i < 2^12)
+    const unsigned rcp20 = ((1u << 20) + (unsigned)nsc - 1u) / (unsigned)nsc;
+    for (int i = tid; i < nsr * nsc; i += 256) {
+        const int r = (int)(((unsigned)i * rcp20) >> 20), c = i - r * nsc;
+        const int gy = clampi(sy_lo + r, 0, p.sh - 1) - p.src_row0;
+        const int gx = clampi(sx_lo + c, 0, p.sw - 1);
+        const uint8_t* px = p.src + (size_t)gy * p.src_stride + 3 * (size_t)gx;
+        int c0 = px[0], c1 = px[1], c2 = px[2];
+        int B = p.swapRB ? c2 : c0, R = p.swapRB ? c0 : c2;
+        int Y, Cr, Cb;
+        bgr_to_ycc(B, c1, R, Y, Cr, Cb);
+        sP[0][r][c] = (uint8_t)Y;
+        sP[1][r][c] = (uint8_t)Cr;
+        sP[2][r][c] = (uint8_t)Cb;
     }
     __syncthreads();
 
