@@ -1,5 +1,5 @@
 cd /root/repo
-for r in 1 2; do for lib in build/alt/lib_oldA.so build/alt/lib_new.so; do
+for r in 1 2; do for lib in build/alt/lib_*.so; do
 SRCNN_B200_LIB=$PWD/$lib python bench.py --steps 50 --warmup 5 --no-cpu 2>/dev/null | python -c "
 import sys,json
 for l in sys.stdin:
