@@ -137,6 +137,22 @@ def time_cpu(run, budget_s=12.0):
     return px / dt / 1e6, "%dx%d crop of the 1080p frame -> %dx%d (%.2f MPix out, %.1f s)" % (w, h, out.shape[1], out.shape[0], px / 1e6, dt), dt
 
 
+def time_cpu_makefile_flags(budget_s=4.0):
+    """The same CPU code as the reference's own Makefile really builds it (no -O flag on the compile lines, Makefile:21-23,43):
+    oracle/_ref/libref_O0.so, bit-identical output, ~10x slower.  A small bounded sample; None when that build is absent."""
+    try:
+        from oracle.oracle import RefLib, cv2_pipeline
+        ref = RefLib("O0")
+    except Exception:
+        return None
+
+    def run(img):
+        return cv2_pipeline(img, SCALE, ref.cnn)
+    v, sample, _ = time_cpu(run, budget_s)
+    return {"value": v, "unit": UNIT, "cores": ref.threads(), "sample": sample,
+            "what": "same sources with the reference Makefile's own compile flags (-mtune=native -fopenmp, no -O)"}
+
+
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
@@ -289,6 +305,8 @@ def run_ours(args, rank, world, local_rank):
             run, kind, threads, desc = cpu_reference_runner()
             v, sample, _ = time_cpu(run, args.cpu_budget)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample, "what": desc}
+            if kind == "reference":   # also as the reference's Makefile builds it
+                line["cpu_baseline"]["makefile_flags"] = time_cpu_makefile_flags()
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line), flush=True)
