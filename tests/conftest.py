@@ -46,6 +46,14 @@ def engine():
     assert torch.cuda.is_available(), "gpu tests need a CUDA device"
     import srcnn_cpp_b200 as S
     eng = S.Engine(device=0, variant=S.VARIANT_TC)
+    # The context's own stream is non-blocking: it does not order itself against torch's default stream, so a test's
+    # torch.zeros / copy_ could still be in flight when a kernel of ours reads or writes the same tensor (seen as an all-zero
+    # result under compute-sanitizer, whose slower kernels widen the window).  One torch stream for both sides instead:
+    # everything a test does on the device is then in stream order.
+    st = torch.cuda.Stream(device=0)
+    torch.cuda.synchronize()
+    torch.cuda.set_stream(st)
+    eng.set_stream(st.cuda_stream)
     yield eng
     eng.close()
 
