@@ -4,7 +4,9 @@ os.environ["SRCNN_TC_DEBUG"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import srcnn_cpp_b200 as S
-eng = S.Engine(0)
+st = torch.cuda.Stream()
+torch.cuda.set_stream(st)   # torch and the context on one stream
+eng = S.Engine(0, stream=st.cuda_stream)
 y = torch.randint(0, 256, (2160, 3840), dtype=torch.uint8, device="cuda")
 out = torch.zeros_like(y)
 for _ in range(3):
