@@ -115,3 +115,89 @@ def test_cfg5_x4_frame_invariants(engine, oracle):
     got = engine.process(small, 4.0)
     st = diff_stats(got, oracle.pipeline(small, 4.0))
     assert st["max"] <= 3 and st["le1"] >= 0.999, st
+
+
+def test_cfg4_full_size_32768_squared(engine):
+    """configs[3] at its FULL size: one 32768x32768 -> 65536x65536 image (2^32 output pixels, 12.9 GB of BGR, 529 strips) on
+    one GPU.  Checked through size-independent properties where 32-bit index arithmetic would break first:
+      * a full-width row band far down the image (output rows 60000..60512, byte offsets beyond 2^33) == the same rows of the
+        whole-image run, bit for bit;
+      * a 400x400 source window deep inside the image, processed as an image of its own, == the whole-image result on the
+        window's interior (the window starts on a source row that is a multiple of 11, so every output row keeps its ring
+        slot and therefore its summation order in the tcgen05 kernel);
+      * the four image corners are finite, non-constant data (no tile was skipped)."""
+    import torch
+    import srcnn_cpp_b200 as S
+    free, _ = torch.cuda.mem_get_info()
+    if free < 48 * 2**30:
+        pytest.skip("needs ~36 GB of device memory")
+    SW = SH = 32768
+    OW = OH = 65536
+    g = torch.Generator(device="cuda:0")
+    g.manual_seed(44)
+    # smooth-ish content: low-resolution noise repeated 64x in both directions plus fine grain (all on the device)
+    base = torch.randint(0, 256, (SH // 64, SW // 64, 3), dtype=torch.uint8, device="cuda:0", generator=g)
+    src = base.repeat_interleave(64, 0).repeat_interleave(64, 1)
+    src += torch.randint(0, 24, (SH, SW, 3), dtype=torch.uint8, device="cuda:0", generator=g)   # wraps at 255: fine, still bytes
+    del base
+    whole = torch.empty((OH, OW, 3), dtype=torch.uint8, device="cuda:0")
+    engine.process_device(src, 2.0, whole)
+    engine.sync()
+
+    # (1) a band far down the image
+    r0, r1 = 60000, 60512
+    s0, s1 = S.band_src_rows(SH, 2.0, r0, r1)
+    band = torch.zeros((r1 - r0, OW, 3), dtype=torch.uint8, device="cuda:0")
+    engine.process_band_device(src[s0:s1], SW, SH, s0, s1, 2.0, r0, r1, band)
+    engine.sync()
+    assert torch.equal(whole[r0:r1], band)
+
+    # (2) a window deep inside, as an image of its own
+    sy0, sx0, n = 11 * 2727, 31000, 400
+    win = src[sy0:sy0 + n, sx0:sx0 + n].contiguous()
+    out = torch.zeros((2 * n, 2 * n, 3), dtype=torch.uint8, device="cuda:0")
+    engine.process_device(win, 2.0, out)
+    engine.sync()
+    m = 16   # bicubic reach (4 output px) + the CNN's 6-px halo, rounded up
+    ref = whole[2 * sy0 + m:2 * (sy0 + n) - m, 2 * sx0 + m:2 * (sx0 + n) - m]
+    assert torch.equal(out[m:-m, m:-m], ref)
+
+    # (3) corners
+    for ys in (slice(0, 64), slice(OH - 64, OH)):
+        for xs in (slice(0, 64), slice(OW - 64, OW)):
+            c = whole[ys, xs].float()
+            assert torch.isfinite(c).all() and float(c.std()) > 1.0
+    del whole, src, band
+    torch.cuda.empty_cache()
+
+
+def test_cfg3_full_size_batch_of_1024_frames(engine):
+    """configs[2] at its FULL size: 1024 frames of 1280x720 -> 2560x1440 in ONE batch call (2.8 GB in, 11.3 GB out).  Frame k is
+    frame 0 rolled by 3 (k mod 97) source columns, so every result is known from frame 0's: the batch call must equal
+    single-frame calls bit for bit on sampled frames (first, last, some in between), and the roll relation must hold away from
+    the left/right borders for all sampled frames (a frame that was skipped, repeated or written to the wrong slot breaks it)."""
+    import torch
+    free, _ = torch.cuda.mem_get_info()
+    if free < 24 * 2**30:
+        pytest.skip("needs ~16 GB of device memory")
+    rng = np.random.default_rng(33)
+    base = torch.from_numpy(_synth(rng, 720, 1280)).to("cuda:0")
+    N = 1024
+    shifts = [3 * (k % 97) for k in range(N)]
+    src = torch.empty((N, 720, 1280, 3), dtype=torch.uint8, device="cuda:0")
+    for k in range(N):
+        src[k] = torch.roll(base, shifts[k], dims=1)
+    dst = torch.zeros((N, 1440, 2560, 3), dtype=torch.uint8, device="cuda:0")
+    engine.process_batch_device(src, 2.0, dst)
+    engine.sync()
+    one = torch.zeros((1440, 2560, 3), dtype=torch.uint8, device="cuda:0")
+    for k in (0, 1, 511, 777, 1023):
+        engine.process_device(src[k], 2.0, one)
+        engine.sync()
+        assert torch.equal(dst[k], one), k
+    ref = dst[0]
+    for k in range(0, N, 37):
+        want = torch.roll(ref, 2 * shifts[k], dims=1)
+        assert torch.equal(dst[k][:, 640:-640], want[:, 640:-640]), k
+    del src, dst
+    torch.cuda.empty_cache()
