@@ -9,12 +9,13 @@
 //     item is a vertical strip of 124 output columns (lanes 2..125; +-2 lanes are conv3's horizontal reach)
 //     walked top to bottom, one image row per step.
 //   * conv1 is a dense im2col GEMM whose A operand lives in TENSOR MEMORY as a rolling ring: for every new image
-//     row each lane packs its 9 horizontal taps (Y[r][c-4..c+4], FP16) into a 5-column slot of a 10-slot ring
+//     row each lane packs its 9 horizontal taps (Y[r][c-4..c+4], FP16) into a 5-column slot of an 11-slot ring
 //     (tcgen05.st); conv1 of output row r reads the nine slots of rows r-4..r+4 -- 7 x (M128 N64 K16) MMAs with
-//     A from TMEM, K = 112 (90 taps + bias + padding), against one of ten pre-rotated weight images (which slot
-//     holds which kernel row depends on r mod 10).  Each pixel's taps are written ONCE and reused by nine rows,
-//     so conv1 executes 14 336 FLOP/px instead of the 20 480 of a Toeplitz-weight GEMM off shared memory, and
-//     its A operand never touches the shared-memory port.
+//     A from TMEM, K = 112 (90 taps + bias + padding), against one of eleven pre-rotated weight images (which slot
+//     holds which kernel row depends on r mod 11; the slot is chosen by ABSOLUTE image row, so a row's summation
+//     order does not depend on how the image is cut into strips, segments or bands).  Each pixel's taps are written
+//     ONCE and reused by nine rows, so conv1 executes 14 336 FLOP/px instead of the 20 480 of a Toeplitz-weight GEMM
+//     off shared memory, and its A operand never touches the shared-memory port.
 //   * The bias of conv1 sits in the K padding (a constant-ones ring column times hi+lo FP16 bias rows); conv2
 //     borrows the same ones column for its bias MMA.  Epilogues are pure ReLU + FP16 pack.
 //   * conv2 = 4+1 x (M128 N32 K16) with A = packed activations written back to TMEM in place; conv3 = "tap
@@ -24,11 +25,14 @@
 //   * The reference's two border clamps are reproduced exactly: conv1 reads the replicate-clamped Y (applied
 //     when a row is staged), conv3 reads act2 AT THE CLAMPED PIXEL (src/srcnn.cpp:203,209) -- out-of-image taps
 //     fold onto the edge row of T, the horizontal exchange clamps its lane index; never by padding Y.
-//   * Warp specialisation by PHASE, not by tile: per strip pipeline one warpgroup does E1 (D1 -> ReLU/pack ->
-//     A1), one does E2 (D2 -> A2) plus the im2col ring producer, one does E3 (tap sums, exchange, store), and one
-//     elected lane of an issuer warp issues every MMA of the pipeline in order (with warp-uniform control flow a
-//     single thread issues tcgen05.mma at the tensor-pipe rate; tools/microbench/mma_rate5.cu).  Three rows
-//     ("units", 64 TMEM columns each) are in flight per pipeline, two pipelines per CTA share the tensor pipe.
+//   * Warp specialisation by PHASE, not by tile: per strip pipeline four warpgroups, one thread per TMEM lane in
+//     each -- the im2col ring producer, E1 (D1 -> ReLU/pack -> A1), E2 (D2 -> A2) and E3 (tap sums, exchange,
+//     store).  The MMAs of a stage are issued by one elected lane of one warp of the warpgroup that produced their
+//     A operand (with warp-uniform control flow a single thread issues tcgen05.mma at the tensor-pipe rate;
+//     tools/microbench/mma_rate5.cu).  Three rows ("units", 64 TMEM columns each) are in flight per pipeline, two
+//     pipelines per CTA share the tensor pipe.
+//   * The (strip, row) steps are cut over the pipelines by cost (tc2_partition below): a pipeline's piece of one
+//     strip pays for its halo rows and its drain, so pieces that cross a strip boundary get fewer rows.
 //
 // Executed tensor work per pixel: conv1 2*112*64 = 14 336, conv2 2*80*32 = 5 120, conv3 2*32*32 = 2 048 FLOP
 // (x 128/124 for the strip halo); algorithmic 16 064 FLOP/px is what bench.py reports against the roofline.
