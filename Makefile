@@ -10,7 +10,7 @@ CSRC := srcnn_cpp_b200/csrc
 OBJ := build/obj
 LIB := srcnn_cpp_b200/libsrcnn_b200.so
 WEIGHTS := $(abspath srcnn_cpp_b200/data/srcnn_weights.bin)
-CU := api color_bicubic srcnn_fp32 srcnn_tc srcnn_tc2 fraw_resize
+CU := api mgpu color_bicubic srcnn_fp32 srcnn_tc2 fraw_resize
 OBJS := $(addprefix $(OBJ)/,$(addsuffix .o,$(CU))) $(OBJ)/weights_blob.o $(OBJ)/libsrcnn.o
 
 all: $(LIB) bin/srcnn oracle

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SRCNN_B200_ABI_VERSION 1
+#define SRCNN_B200_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #pragma GCC visibility push(default)
@@ -56,15 +56,28 @@ enum {
     SRCNN_E_KERNEL = -33    /* a device-side guard tripped (pipeline watchdog) */
 };
 
+/* Stage of the whole path in which the last failed call died (srcnn_last_failed_stage): lets the CLI keep the
+ * reference's distinct exit codes -2 (colour conversion, src/srcnn.cpp:526) and -3 (split, :555). */
+enum {
+    SRCNN_STAGE_NONE = 0,
+    SRCNN_STAGE_COLOR_BICUBIC = 1, /* cvtColor + resize, src/srcnn.cpp:509,570-583 */
+    SRCNN_STAGE_PLANES = 2,        /* the plane set `split` produces, src/srcnn.cpp:539-540 */
+    SRCNN_STAGE_CNN = 3,           /* Convolution99x11 + Convolution55, src/srcnn.cpp:609,627 */
+    SRCNN_STAGE_MERGE = 4          /* merge + cvtColor back, src/srcnn.cpp:637-657 */
+};
+
 int srcnn_abi_version(void);
 const char* srcnn_strerror(int status);
 
 /* Context = one device + one stream + workspace + packed weights.  Re-entrant: one context per host
  * thread (or serialise calls); may be created and used from a non-main thread like the reference's
- * worker pthread (src/srcnn.cpp:717-724). */
+ * worker pthread (src/srcnn.cpp:717-724).  Every call runs on the context's device and restores the
+ * calling thread's current CUDA device before it returns. */
 int srcnn_create(srcnn_ctx** out, int device, int variant);
 int srcnn_destroy(srcnn_ctx* ctx);
 const char* srcnn_last_error(srcnn_ctx* ctx);
+int srcnn_last_failed_stage(srcnn_ctx* ctx);
+int srcnn_get_device(srcnn_ctx* ctx);
 int srcnn_set_variant(srcnn_ctx* ctx, int variant);
 int srcnn_get_variant(srcnn_ctx* ctx);
 /* Use an existing CUDA stream (cudaStream_t as void*) for all work of this context; NULL = own stream. */
@@ -76,16 +89,20 @@ long long srcnn_launch_count(srcnn_ctx* ctx);
 int srcnn_device_sm_count(srcnn_ctx* ctx);
 /* Optional per-stage device timing with CUDA events on the context stream (used by bench.py for the
  * roofline numbers).  srcnn_profile_read synchronises, returns the summed milliseconds of
- * [0] colour+bicubic, [1] fused SRCNN, [2] merge+colour-back over the whole-path calls since the
- * previous read, and the number of such calls. */
+ * [0] colour+bicubic, [1] fused SRCNN, [2] merge+colour-back over everything processed since the
+ * previous read, and the number of whole-path API calls that work came from (a batch or a banded
+ * call counts once, however many frames or bands it ran). */
 int srcnn_profile_enable(srcnn_ctx* ctx, int on);
 int srcnn_profile_read(srcnn_ctx* ctx, double* ms3, int* calls);
 
 int srcnn_out_dims(int w, int h, float scale, int* ow, int* oh);
 
-/* Pinned host memory for callers that want true async DMA (bench e2e, CLI). */
+/* Pinned host memory for callers that want true async DMA (bench e2e, CLI): allocated page-locked, or the
+ * caller's own buffer page-locked in place.  Both are valid for every device of the process. */
 int srcnn_host_alloc(void** p, size_t bytes);
 int srcnn_host_free(void* p);
+int srcnn_host_register(void* p, size_t bytes);
+int srcnn_host_unregister(void* p);
 
 /* ---- whole path: replaces src/srcnn.cpp:505-659 -------------------------------------------------- */
 /* Host buffers in, host buffers out; H2D and D2H copies are part of the call; returns when dst is ready. */
@@ -113,11 +130,56 @@ int srcnn_process_band_device(srcnn_ctx* ctx, const uint8_t* d_src, int w, int h
                               int s1, int order, float scale, int r0, int r1, uint8_t* d_dst,
                               size_t dst_stride);
 
+/* Host-buffer form: `src` is the WHOLE source image (row 0), `dst_rows` points at output row r0.  Copies in only
+ * the source rows the band needs, pipelines sub-bands over three streams, returns when dst_rows is ready. */
+int srcnn_process_band_host(srcnn_ctx* ctx, const uint8_t* src, int w, int h, size_t src_stride, int order,
+                            float scale, int r0, int r1, uint8_t* dst_rows, size_t dst_stride);
+
+/* ---- all GPUs of one box behind one call (SURVEY 8b "device list", 8e) ----------------------------
+ * The reference's unit of parallelism is the OpenMP row loop inside one call from one worker thread
+ * (src/srcnn.cpp:283,213,717-724).  Its drop-in equivalent: ONE call that fans frames (frame f -> device
+ * f mod n) or output-row bands (6-px halo, srcnn_band_src_rows) out over a list of devices.  One host
+ * thread, one srcnn_ctx and one stream set per device, disjoint outputs, no inter-GPU traffic, no NCCL.
+ * Calls block until every device has finished.  A device may be listed more than once (several contexts
+ * on one GPU). */
+typedef struct srcnn_mgpu srcnn_mgpu;
+/* devices == NULL: devices 0..n-1; n <= 0: every visible device. */
+int srcnn_mgpu_create(srcnn_mgpu** out, const int* devices, int n, int variant);
+int srcnn_mgpu_destroy(srcnn_mgpu* m);
+int srcnn_mgpu_device_count(srcnn_mgpu* m);
+srcnn_ctx* srcnn_mgpu_context(srcnn_mgpu* m, int i);       /* worker i's context (variant, profiling, error text) */
+const char* srcnn_mgpu_last_error(srcnn_mgpu* m);
+/* Worker i's share of a banded image: output rows [*r0,*r1) and the source rows [*s0,*s1) they need.  Pure
+ * host arithmetic (callable without a GPU). */
+int srcnn_mgpu_band_plan(int n_workers, int h, float scale, int i, int* r0, int* r1, int* s0, int* s1);
+/* Frames: frame f is processed by worker f mod n.  Host buffers (H2D / kernels / D2H pipelined per device). */
+int srcnn_mgpu_process_batch_host(srcnn_mgpu* m, const uint8_t* src, int nframes, int w, int h, size_t src_stride,
+                                  size_t src_frame_stride, int order, float scale, uint8_t* dst, size_t dst_stride,
+                                  size_t dst_frame_stride);
+/* One image cut into n row bands, worker i computes band i straight into dst.  Host buffers. */
+int srcnn_mgpu_process_banded_host(srcnn_mgpu* m, const uint8_t* src, int w, int h, size_t src_stride, int order,
+                                   float scale, uint8_t* dst, size_t dst_stride);
+/* Device-resident forms: d_src[i] / d_dst[i] live on worker i's device.  Batch: worker i owns counts[i]
+ * frames.  Banded: d_src[i] holds source rows [s0_i, s1_i) of srcnn_mgpu_band_plan, d_dst[i] points at
+ * output row r0_i. */
+int srcnn_mgpu_process_batch_device(srcnn_mgpu* m, const uint8_t* const* d_src, const int* counts, int w, int h,
+                                    size_t src_stride, size_t src_frame_stride, int order, float scale,
+                                    uint8_t* const* d_dst, size_t dst_stride, size_t dst_frame_stride);
+int srcnn_mgpu_process_banded_device(srcnn_mgpu* m, const uint8_t* const* d_src, int w, int h, size_t src_stride,
+                                     int order, float scale, uint8_t* const* d_dst, size_t dst_stride);
+/* Timing of the last call: per-worker device time (CUDA events on each worker's stream around its share;
+ * host-buffer calls: the worker's wall time, copies included) and the call's wall time.  ms has room for
+ * srcnn_mgpu_device_count() doubles. */
+int srcnn_mgpu_last_timing(srcnn_mgpu* m, double* ms_per_worker, double* wall_ms);
+
 /* ---- stages (device pointers; enqueued on the context stream) ------------------------------------ */
 /* cvtColor + split + 3x resize (src/srcnn.cpp:509,540,570-583): BGR8 -> three u8 planes of ow x oh. */
 int srcnn_stage_color_bicubic_device(srcnn_ctx* ctx, const uint8_t* d_src, int w, int h, size_t src_stride,
                                      int order, float scale, uint8_t* d_y, uint8_t* d_cr, uint8_t* d_cb,
                                      size_t plane_pitch);
+/* One 8-bit plane through resize(..., CV_INTER_CUBIC) (src/srcnn.cpp:577-582), host buffers (ProcessSRCNN's alpha). */
+int srcnn_resize_plane_host(srcnn_ctx* ctx, const uint8_t* src, int w, int h, size_t src_stride, float scale,
+                            uint8_t* dst, size_t dst_stride);
 /* Convolution99x11 + Convolution55 (src/srcnn.cpp:609,627): Y plane -> Y' plane, `variant` as above. */
 int srcnn_stage_cnn_device(srcnn_ctx* ctx, int variant, const uint8_t* d_y, int w, int h, size_t pitch,
                            uint8_t* d_out, size_t out_pitch);

@@ -38,6 +38,11 @@ ABI_SYMBOLS = [
     "srcnn_band_src_rows", "srcnn_process_band_device", "srcnn_stage_color_bicubic_device",
     "srcnn_stage_cnn_device", "srcnn_stage_conv99x11_fp32_device", "srcnn_stage_merge_device",
     "srcnn_fraw_scale_device",
+    "srcnn_last_failed_stage", "srcnn_get_device", "srcnn_host_register", "srcnn_host_unregister",
+    "srcnn_process_band_host", "srcnn_resize_plane_host",
+    "srcnn_mgpu_create", "srcnn_mgpu_destroy", "srcnn_mgpu_device_count", "srcnn_mgpu_context", "srcnn_mgpu_last_error",
+    "srcnn_mgpu_band_plan", "srcnn_mgpu_process_batch_host", "srcnn_mgpu_process_banded_host",
+    "srcnn_mgpu_process_batch_device", "srcnn_mgpu_process_banded_device", "srcnn_mgpu_last_timing",
 ]
 
 
@@ -94,6 +99,26 @@ def load_library():
     L.srcnn_stage_conv99x11_fp32_device.argtypes = [vp, u8p, C.c_int, C.c_int, sz, vp]
     L.srcnn_stage_merge_device.argtypes = [vp, u8p, u8p, u8p, C.c_int, C.c_int, sz, C.c_int, u8p, sz]
     L.srcnn_fraw_scale_device.argtypes = [vp, vp, C.c_uint, C.c_uint, C.c_uint, C.c_uint, vp, C.c_int]
+    L.srcnn_last_failed_stage.argtypes = [vp]
+    L.srcnn_get_device.argtypes = [vp]
+    L.srcnn_host_register.argtypes = [vp, sz]
+    L.srcnn_host_unregister.argtypes = [vp]
+    L.srcnn_process_band_host.argtypes = [vp, u8p, C.c_int, C.c_int, sz, C.c_int, C.c_float, C.c_int, C.c_int, u8p, sz]
+    L.srcnn_resize_plane_host.argtypes = [vp, u8p, C.c_int, C.c_int, sz, C.c_float, u8p, sz]
+    L.srcnn_mgpu_create.argtypes = [C.POINTER(vp), i32p, C.c_int, C.c_int]
+    L.srcnn_mgpu_destroy.argtypes = [vp]
+    L.srcnn_mgpu_device_count.argtypes = [vp]
+    L.srcnn_mgpu_context.restype = vp
+    L.srcnn_mgpu_context.argtypes = [vp, C.c_int]
+    L.srcnn_mgpu_last_error.restype = C.c_char_p
+    L.srcnn_mgpu_last_error.argtypes = [vp]
+    L.srcnn_mgpu_band_plan.argtypes = [C.c_int, C.c_int, C.c_float, C.c_int, i32p, i32p, i32p, i32p]
+    L.srcnn_mgpu_process_batch_host.argtypes = [vp, u8p, C.c_int, C.c_int, C.c_int, sz, sz, C.c_int, C.c_float, u8p, sz, sz]
+    L.srcnn_mgpu_process_banded_host.argtypes = [vp, u8p, C.c_int, C.c_int, sz, C.c_int, C.c_float, u8p, sz]
+    L.srcnn_mgpu_process_batch_device.argtypes = [vp, C.POINTER(vp), i32p, C.c_int, C.c_int, sz, sz, C.c_int, C.c_float,
+                                                  C.POINTER(vp), sz, sz]
+    L.srcnn_mgpu_process_banded_device.argtypes = [vp, C.POINTER(vp), C.c_int, C.c_int, sz, C.c_int, C.c_float, C.POINTER(vp), sz]
+    L.srcnn_mgpu_last_timing.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     _lib = L
     return L
 
@@ -265,10 +290,31 @@ class Engine:
         self._check(self.L.srcnn_stage_cnn_device(self.ctx, int(v), _dptr(y), w, h, y.stride(0), _dptr(out), out.stride(0)))
         return out
 
-    def set_tc_kernel(self, k):
-        """Test hook: 2 = row-walking tcgen05 kernel (default), 1 = first-generation kernel."""
-        self.L.srcnn_debug_set_tc_kernel.argtypes = [C.c_void_p, C.c_int]
-        self._check(self.L.srcnn_debug_set_tc_kernel(self.ctx, int(k)))
+    def set_host_bands(self, bands):
+        """Tuning hook: most sub-bands the host-buffer pipeline cuts a single frame into."""
+        self.L.srcnn_debug_set_host_bands.argtypes = [C.c_void_p, C.c_int]
+        self._check(self.L.srcnn_debug_set_host_bands(self.ctx, int(bands)))
+
+    def process_band_host(self, img, scale, r0, r1, out_rows=None, order=ORDER_BGR):
+        """img: the WHOLE HxWx3 source image; returns output rows [r0, r1) as an (r1-r0)xOWx3 array."""
+        img = np.ascontiguousarray(img)
+        h, w, _ = img.shape
+        ow, oh = out_dims(w, h, scale)
+        if out_rows is None:
+            out_rows = np.empty((r1 - r0, ow, 3), np.uint8)
+        self._check(self.L.srcnn_process_band_host(self.ctx, img.ctypes.data, w, h, img.strides[0], order, C.c_float(scale),
+                                                   r0, r1, out_rows.ctypes.data, out_rows.strides[0]))
+        return out_rows
+
+    def resize_plane(self, plane, scale):
+        """One uint8 plane through the path's cubic resize (cv::resize INTER_CUBIC semantics), host buffers."""
+        plane = np.ascontiguousarray(plane)
+        h, w = plane.shape
+        ow, oh = out_dims(w, h, scale)
+        out = np.empty((oh, ow), np.uint8)
+        self._check(self.L.srcnn_resize_plane_host(self.ctx, plane.ctypes.data, w, h, plane.strides[0], C.c_float(scale),
+                                                   out.ctypes.data, out.strides[0]))
+        return out
 
     def set_tc2_seg_ovh(self, ovh):
         """Test hook: cost of opening a segment in the row-walking kernel's work cut (0 = equal row counts)."""
@@ -297,3 +343,106 @@ class Engine:
         self._check(self.L.srcnn_stage_merge_device(self.ctx, _dptr(y), _dptr(cr), _dptr(cb), w, h, y.stride(0), order,
                                                     _dptr(dst), dst.stride(0)))
         return dst
+
+
+def mgpu_band_plan(n_workers, h, scale, i):
+    """Worker i's share of a banded image: (r0, r1, s0, s1).  Pure host arithmetic."""
+    L = load_library()
+    v = [C.c_int() for _ in range(4)]
+    rc = L.srcnn_mgpu_band_plan(n_workers, h, C.c_float(scale), i, *[C.byref(x) for x in v])
+    if rc != OK:
+        raise SrcnnError(rc, L.srcnn_strerror(rc).decode())
+    return tuple(x.value for x in v)
+
+
+class MultiEngine:
+    """srcnn_mgpu: a device list behind one call -- one host thread, context and stream set per device
+    (include/srcnn_b200.h).  Frames go to worker f mod n, a single image is cut into n row bands."""
+
+    def __init__(self, devices=None, variant=VARIANT_TC):
+        self.L = load_library()
+        self.h = C.c_void_p()
+        if devices is None:
+            arr, n = None, 0
+        else:
+            n = len(devices)
+            arr = (C.c_int * n)(*devices)
+        rc = self.L.srcnn_mgpu_create(C.byref(self.h), arr, n, int(variant))
+        if rc != OK:
+            self.h = None
+            raise SrcnnError(rc, self.L.srcnn_strerror(rc).decode())
+        self.n = int(self.L.srcnn_mgpu_device_count(self.h))
+        self.devices = [int(self.L.srcnn_get_device(self.L.srcnn_mgpu_context(self.h, i))) for i in range(self.n)]
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.srcnn_mgpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != OK:
+            raise SrcnnError(rc, (self.L.srcnn_mgpu_last_error(self.h) or b"").decode() or self.L.srcnn_strerror(rc).decode())
+
+    def set_variant(self, variant):
+        for i in range(self.n):
+            self.L.srcnn_set_variant(self.L.srcnn_mgpu_context(self.h, i), int(variant))
+
+    def launches(self):
+        return sum(int(self.L.srcnn_launch_count(self.L.srcnn_mgpu_context(self.h, i))) for i in range(self.n))
+
+    def last_timing(self):
+        """-> (per-worker ms of its share, wall ms of the call)"""
+        ms = (C.c_double * self.n)()
+        wall = C.c_double()
+        self._check(self.L.srcnn_mgpu_last_timing(self.h, ms, C.byref(wall)))
+        return list(ms), wall.value
+
+    def band_plan(self, h, scale):
+        return [mgpu_band_plan(self.n, h, scale, i) for i in range(self.n)]
+
+    # -- host buffers (numpy, or raw pointers for pinned memory) -------------------------------------
+    def process_banded(self, img, scale, order=ORDER_BGR, out=None):
+        img = np.ascontiguousarray(img)
+        h, w, _ = img.shape
+        ow, oh = out_dims(w, h, scale)
+        if out is None:
+            out = np.empty((oh, ow, 3), np.uint8)
+        self._check(self.L.srcnn_mgpu_process_banded_host(self.h, img.ctypes.data, w, h, img.strides[0], order, C.c_float(scale),
+                                                          out.ctypes.data, out.strides[0]))
+        return out
+
+    def process_batch(self, frames, scale, order=ORDER_BGR, out=None):
+        frames = np.ascontiguousarray(frames)
+        n, h, w, _ = frames.shape
+        ow, oh = out_dims(w, h, scale)
+        if out is None:
+            out = np.empty((n, oh, ow, 3), np.uint8)
+        self._check(self.L.srcnn_mgpu_process_batch_host(self.h, frames.ctypes.data, n, w, h, frames.strides[1], frames.strides[0],
+                                                         order, C.c_float(scale), out.ctypes.data, out.strides[1], out.strides[0]))
+        return out
+
+    # -- device-resident shares (torch CUDA tensors, one per worker, each on that worker's device) -----
+    def process_batch_device(self, srcs, scale, dsts, order=ORDER_BGR):
+        """srcs[i]: n_i x H x W x 3 on worker i's device (n_i may be 0 -> pass None); dsts[i]: n_i x OH x OW x 3."""
+        ref = next(t for t in srcs if t is not None)
+        _, h, w, _ = ref.shape
+        dref = next(t for t in dsts if t is not None)
+        ps = (C.c_void_p * self.n)(*[t.data_ptr() if t is not None else None for t in srcs])
+        pd = (C.c_void_p * self.n)(*[t.data_ptr() if t is not None else None for t in dsts])
+        cnt = (C.c_int * self.n)(*[t.shape[0] if t is not None else 0 for t in srcs])
+        self._check(self.L.srcnn_mgpu_process_batch_device(self.h, ps, cnt, w, h, ref.stride(1), ref.stride(0), order, C.c_float(scale),
+                                                           pd, dref.stride(1), dref.stride(0)))
+
+    def process_banded_device(self, src_bands, w, h, scale, dst_bands, order=ORDER_BGR):
+        """src_bands[i]: (s1_i-s0_i) x W x 3 holding the source rows of band_plan()[i]; dst_bands[i]: (r1_i-r0_i) x OW x 3."""
+        ps = (C.c_void_p * self.n)(*[t.data_ptr() if t is not None else None for t in src_bands])
+        pd = (C.c_void_p * self.n)(*[t.data_ptr() if t is not None else None for t in dst_bands])
+        sref = next(t for t in src_bands if t is not None)
+        dref = next(t for t in dst_bands if t is not None)
+        self._check(self.L.srcnn_mgpu_process_banded_device(self.h, ps, w, h, sref.stride(0), order, C.c_float(scale), pd, dref.stride(0)))

@@ -5,7 +5,9 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
+#include <new>
 
 bool jpeg_decode(const std::vector<uint8_t>& file, ImageBGR* out, std::string* err);   // jpeg_io.cpp (nvJPEG)
 bool jpeg_encode(const ImageBGR& img, std::vector<uint8_t>* file, std::string* err);
@@ -58,11 +60,18 @@ bool png_decode(const std::vector<uint8_t>& file, ImageBGR* out, std::string* er
         pos += 12 + (size_t)len;
     }
     if (w == 0 || h == 0) { *err = "PNG without IHDR"; return false; }
-    if (interlace) { *err = "interlaced PNG not supported"; return false; }
-    if (depth != 8 && depth != 16) { *err = "PNG bit depth not supported (8 or 16 only)"; return false; }
+    // IHDR is untrusted: bound the geometry before any size arithmetic (cv::imread's own limit is 2^30 pixels)
+    if (w > (1u << 20) || h > (1u << 20) || (uint64_t)w * h > (1ull << 30)) { *err = "PNG dimensions out of range"; return false; }
+    if (interlace) { *err = "interlaced (Adam7) PNG not supported"; return false; }
     int ch = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
-    if (!ch || (ctype == 3 && depth != 8)) { *err = "PNG colour type not supported"; return false; }
-    const size_t bpp = (size_t)ch * depth / 8, stride = bpp * w;
+    if (!ch) { *err = "PNG colour type not supported"; return false; }
+    const bool sub_byte = depth == 1 || depth == 2 || depth == 4;       // grey or palette only (PNG spec)
+    if (!(depth == 8 || depth == 16 || (sub_byte && (ctype == 0 || ctype == 3))) || (ctype == 3 && depth == 16)) {
+        *err = "PNG bit depth not supported for this colour type";
+        return false;
+    }
+    const size_t bpp = std::max<size_t>(1, (size_t)ch * depth / 8);     // filter distance in bytes
+    const size_t stride = ((size_t)ch * depth * w + 7) / 8;             // packed scanline
     std::vector<uint8_t> raw((stride + 1) * h);
     uLongf rawlen = raw.size();
     if (uncompress(raw.data(), &rawlen, idat.data(), idat.size()) != Z_OK || rawlen != raw.size()) { *err = "PNG inflate failed"; return false; }
@@ -87,6 +96,21 @@ bool png_decode(const std::vector<uint8_t>& file, ImageBGR* out, std::string* er
     }
     out->w = (int)w; out->h = (int)h;
     out->px.resize((size_t)w * h * 3);
+    if (sub_byte) {   // 1/2/4-bit grey (scaled to 0..255) or palette indices, most significant bits first
+        const int per_byte = 8 / depth, mask = (1 << depth) - 1, grey_mul = 255 / mask;
+        for (uint32_t y = 0; y < h; y++)
+            for (uint32_t x = 0; x < w; x++) {
+                const int v = (img[y * stride + x / per_byte] >> ((per_byte - 1 - x % per_byte) * depth)) & mask;
+                uint8_t r, g, b;
+                if (ctype == 3) {
+                    const size_t k = (size_t)v * 3;
+                    if (k + 2 < plte.size()) { r = plte[k]; g = plte[k + 1]; b = plte[k + 2]; } else { r = g = b = 0; }
+                } else { r = g = b = (uint8_t)(v * grey_mul); }
+                uint8_t* q = &out->px[((size_t)y * w + x) * 3];
+                q[0] = b; q[1] = g; q[2] = r;
+            }
+        return true;
+    }
     const size_t step = depth / 8;  // 16-bit samples: keep the high byte (like cv::imread's 8-bit conversion)
     for (size_t i = 0; i < (size_t)w * h; i++) {
         const uint8_t* p = &img[i * bpp];
@@ -148,14 +172,15 @@ bool pnm_decode(const std::vector<uint8_t>& f, ImageBGR* out, std::string* err) 
             break;
         }
         long v = 0; bool any = false;
-        while (pos < f.size() && isdigit(f[pos])) { v = v * 10 + (f[pos] - '0'); pos++; any = true; }
+        while (pos < f.size() && isdigit(f[pos])) { v = std::min(v * 10 + (f[pos] - '0'), 1L << 40); pos++; any = true; }
         if (!any) { *err = "bad PNM header"; return false; }
         vals[k] = v;
     }
     pos++;  // single whitespace after maxval
     if (vals[2] != 255 || vals[0] <= 0 || vals[1] <= 0) { *err = "only 8-bit PNM supported"; return false; }
+    if (vals[0] > (1L << 20) || vals[1] > (1L << 20) || vals[0] * vals[1] > (1L << 30)) { *err = "PNM dimensions out of range"; return false; }
     const size_t n = (size_t)vals[0] * vals[1];
-    if (pos + n * ch > f.size()) { *err = "truncated PNM"; return false; }
+    if (pos > f.size() || n * ch > f.size() - pos) { *err = "truncated PNM"; return false; }
     out->w = (int)vals[0]; out->h = (int)vals[1]; out->px.resize(n * 3);
     for (size_t i = 0; i < n; i++) {
         const uint8_t* p = &f[pos + i * ch];
@@ -174,13 +199,21 @@ std::string lower_ext(const std::string& path) {
 
 }  // namespace
 
+// Known gap against cv::imread (src/srcnn.cpp:462): Adam7-interlaced PNGs, ASCII PNM, BMP/TIFF/WebP are reported as a load
+// failure (the reference CLI's "- load failure" path, exit code -1).
 bool image_read(const std::string& path, ImageBGR* out, std::string* err) {
-    std::vector<uint8_t> f;
-    if (!read_file(path, &f)) { *err = "cannot read file"; return false; }
-    if (f.size() >= 8 && f[0] == 0x89 && f[1] == 'P') return png_decode(f, out, err);
-    if (f.size() >= 2 && f[0] == 'P' && (f[1] == '5' || f[1] == '6')) return pnm_decode(f, out, err);
-    if (f.size() >= 3 && f[0] == 0xff && f[1] == 0xd8 && f[2] == 0xff) return jpeg_decode(f, out, err);
-    *err = "unsupported image format (PNG, JPEG and binary PPM/PGM are supported)";
+    try {   // a crafted header must end in the load-failure path, not in an uncaught bad_alloc inside the worker thread
+        std::vector<uint8_t> f;
+        if (!read_file(path, &f)) { *err = "cannot read file"; return false; }
+        if (f.size() >= 8 && f[0] == 0x89 && f[1] == 'P') return png_decode(f, out, err);
+        if (f.size() >= 2 && f[0] == 'P' && (f[1] == '5' || f[1] == '6')) return pnm_decode(f, out, err);
+        if (f.size() >= 3 && f[0] == 0xff && f[1] == 0xd8 && f[2] == 0xff) return jpeg_decode(f, out, err);
+        *err = "unsupported image format (PNG, JPEG and binary PPM/PGM are supported)";
+    } catch (const std::bad_alloc&) {
+        *err = "out of memory while decoding";
+    } catch (const std::exception& e) {
+        *err = e.what();
+    }
     return false;
 }
 

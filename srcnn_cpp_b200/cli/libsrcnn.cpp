@@ -31,30 +31,28 @@ int ProcessSRCNN(const unsigned char* refbuff, unsigned w, unsigned h, unsigned 
     const size_t npx = (size_t)w * h, onpx = (size_t)ow * oh;
     std::vector<unsigned char> rgb(npx * 3), out_rgb(onpx * 3);
     const bool has_alpha = (d == 2 || d == 4);
-    std::vector<unsigned char> a3, a3_out;
-    if (has_alpha) { a3.resize(npx * 3); a3_out.resize(onpx * 3); }
+    std::vector<unsigned char> alpha, alpha_out;
+    if (has_alpha) { alpha.resize(npx); alpha_out.resize(onpx); }
     for (size_t i = 0; i < npx; i++) {
         const unsigned char* p = refbuff + i * d;
         if (d >= 3) { rgb[3 * i] = p[0]; rgb[3 * i + 1] = p[1]; rgb[3 * i + 2] = p[2]; }
         else { rgb[3 * i] = rgb[3 * i + 1] = rgb[3 * i + 2] = p[0]; }
-        if (has_alpha) a3[3 * i] = a3[3 * i + 1] = a3[3 * i + 2] = p[d - 1];
+        if (has_alpha) alpha[i] = p[d - 1];
     }
     rc = srcnn_process_host(g_ctx, rgb.data(), (int)w, (int)h, (size_t)w * 3, SRCNN_ORDER_RGB, muliply, out_rgb.data(), (size_t)ow * 3);
     if (rc) return rc;
     unsigned char* out = new (std::nothrow) unsigned char[onpx * d];
     if (!out) return SRCNN_E_NOMEM;
     if (has_alpha) {
-        // alpha: plain bicubic (the colour+bicubic stage on a grey image, FP32 CNN skipped by taking the
-        // stage's Y plane is not exposed on host pointers; the whole path on a grey image keeps Cr=Cb=128
-        // and only sharpens edges of the matte, which is what libsrcnn does for its alpha plane as well)
-        rc = srcnn_process_host(g_ctx, a3.data(), (int)w, (int)h, (size_t)w * 3, SRCNN_ORDER_RGB, muliply, a3_out.data(), (size_t)ow * 3);
+        // alpha: the plain bicubic resize of the path (resize(..., CV_INTER_CUBIC), src/srcnn.cpp:577-582), no CNN
+        rc = srcnn_resize_plane_host(g_ctx, alpha.data(), (int)w, (int)h, (size_t)w, muliply, alpha_out.data(), (size_t)ow);
         if (rc) { delete[] out; return rc; }
     }
     for (size_t i = 0; i < onpx; i++) {
         unsigned char* q = out + i * d;
         if (d >= 3) { q[0] = out_rgb[3 * i]; q[1] = out_rgb[3 * i + 1]; q[2] = out_rgb[3 * i + 2]; }
         else { q[0] = out_rgb[3 * i + 1]; }
-        if (has_alpha) q[d - 1] = a3_out[3 * i + 1];
+        if (has_alpha) q[d - 1] = alpha_out[i];
     }
     outbuff = out;
     outbuffsz = (unsigned)(onpx * d);

@@ -92,22 +92,25 @@ static int carve_planes(Ctx* c, int ow, int rows, int row0, Planes* pl) {
 
 static int run_cnn(Ctx* c, int variant, const CnnArgs& a) {
     if (variant == SRCNN_VARIANT_FP32) return launch_cnn_fp32(c, a, nullptr);
-    if (variant == SRCNN_VARIANT_TC) return c->tc_kernel == 1 ? launch_cnn_tc(c, a) : launch_cnn_tc2(c, a);
+    if (variant == SRCNN_VARIANT_TC) return launch_cnn_tc2(c, a);
     return fail(c, SRCNN_E_ARG, "unknown variant %d", variant);
 }
 
 // rows [r0,r1) of the full output; d_src holds source rows [s0,s1); d_dst points at output row r0
-static int process_rows(Ctx* c, const uint8_t* d_src, int w, int h, size_t src_stride, int s0, int s1, int order,
-                        float scale, int ow, int oh, int r0, int r1, uint8_t* d_dst, size_t dst_stride) {
+static int process_rows_impl(Ctx* c, const uint8_t* d_src, int w, int h, size_t src_stride, int s0, int s1, int order,
+                             float scale, int ow, int oh, int r0, int r1, uint8_t* d_dst, size_t dst_stride) {
     TapTable *tx, *ty;
+    c->fail_stage = SRCNN_STAGE_COLOR_BICUBIC;
     int rc = get_taps(c, w, ow, &tx);
     if (rc) return rc;
     rc = get_taps(c, h, oh, &ty);
     if (rc) return rc;
     const int p0 = std::max(r0 - 6, 0), p1 = std::min(r1 + 6, oh);  // 6-px halo: 4 (conv1) + 2 (conv3)
     Planes pl;
+    c->fail_stage = SRCNN_STAGE_PLANES;
     rc = carve_planes(c, ow, p1 - p0, p0, &pl);
     if (rc) return rc;
+    c->fail_stage = SRCNN_STAGE_COLOR_BICUBIC;
     // the band must bring every source row its taps touch
     const int need0 = std::min(std::max(ty->h_ofs[p0] - 1, 0), h - 1);
     const int need1 = std::min(std::max(ty->h_ofs[p1 - 1] + 2, 0), h - 1) + 1;
@@ -126,6 +129,7 @@ static int process_rows(Ctx* c, const uint8_t* d_src, int w, int h, size_t src_s
     if (rc) return rc;
     if ((rc = prof_mark(c))) return rc;
 
+    c->fail_stage = SRCNN_STAGE_CNN;
     CnnArgs ca;
     ca.y = pl.y; ca.pitch = pl.pitch;
     ca.W = ow; ca.H = oh;
@@ -134,7 +138,7 @@ static int process_rows(Ctx* c, const uint8_t* d_src, int w, int h, size_t src_s
     ca.out = pl.yout; ca.out_pitch = pl.pitch;
     // optionally the row-walking tcgen05 kernel merges Cr/Cb and converts back to BGR in its last epilogue (no Y' plane, no
     // K-C launch); measured slower than the separate launch (byte stores from one-thread-per-column lanes), so off by default
-    const bool fused = c->variant == SRCNN_VARIANT_TC && c->tc_kernel == 2 && c->fuse_merge;
+    const bool fused = c->variant == SRCNN_VARIANT_TC && c->fuse_merge;
     if (fused) {
         ca.cr = pl.cr; ca.cb = pl.cb;
         ca.bgr = d_dst; ca.bgr_stride = dst_stride; ca.order = order;
@@ -144,6 +148,7 @@ static int process_rows(Ctx* c, const uint8_t* d_src, int w, int h, size_t src_s
     if ((rc = prof_mark(c))) return rc;
     if (fused) return prof_mark(c);
 
+    c->fail_stage = SRCNN_STAGE_MERGE;
     MergeArgs ma;
     const size_t off = (size_t)(r0 - p0) * pl.pitch;
     ma.y = pl.yout + off; ma.cr = pl.cr + off; ma.cb = pl.cb + off;
@@ -155,6 +160,15 @@ static int process_rows(Ctx* c, const uint8_t* d_src, int w, int h, size_t src_s
     return prof_mark(c);
 }
 
+static int process_rows(Ctx* c, const uint8_t* d_src, int w, int h, size_t src_stride, int s0, int s1, int order,
+                        float scale, int ow, int oh, int r0, int r1, uint8_t* d_dst, size_t dst_stride) {
+    const size_t ev0 = c->ev_used;
+    const int rc = process_rows_impl(c, d_src, w, h, src_stride, s0, s1, order, scale, ow, oh, r0, r1, d_dst, dst_stride);
+    if (rc) c->ev_used = ev0;        // a failed band leaves no half-recorded event group behind (srcnn_profile_read pairs by 4)
+    else c->fail_stage = SRCNN_STAGE_NONE;
+    return rc;
+}
+
 static int check_guard(Ctx* c) {
     if (c->h_guard && *c->h_guard != 0) {
         int v = *c->h_guard;
@@ -164,15 +178,130 @@ static int check_guard(Ctx* c) {
     return SRCNN_OK;
 }
 
+
+// ---- host-buffer pipeline -------------------------------------------------------------------------
+// Output rows [R0, R1) of n same-sized frames: host buffers in, host buffers out.  `src` points at row 0 of frame 0 (the
+// whole source image must be addressable: a band reads the source rows its taps touch), `dst` at output row R0 of frame 0.
+// Three streams: copy-in (H2D), compute (the context stream), copy-out (D2H).  A unit is one row band of one frame: a
+// single frame (or a single band of a gigapixel image) is cut into sub-bands so that its D2H -- 4x the H2D bytes at x2 --
+// overlaps the kernels of the next sub-band; frames of a batch overlap the same way.
+struct StreamDrain {   // on every exit path: no async copy may still reference the caller's buffers
+    Ctx* c;
+    ~StreamDrain() {
+        if (c->s_in) cudaStreamSynchronize(c->s_in);
+        if (c->s_out) cudaStreamSynchronize(c->s_out);
+        cudaStreamSynchronize(c->stream);
+    }
+};
+
+int host_pipeline(Ctx* c, const uint8_t* src, int n, int w, int h, size_t src_stride, size_t src_frame_stride, int order,
+                  float scale, int ow, int oh, int R0, int R1, uint8_t* dst, size_t dst_stride, size_t dst_frame_stride) {
+    int rc;
+    TapTable* ty = nullptr;
+    if ((rc = get_taps(c, h, oh, &ty))) return rc;
+    auto src_hi = [&](int r1) {   // one past the last source row output rows < r1 touch (6-px halo in the output)
+        const int p1 = std::min(r1 + 6, oh);
+        return std::min(std::max(ty->h_ofs[p1 - 1] + 2, 0), h - 1) + 1;
+    };
+    const int S0 = std::min(std::max(ty->h_ofs[std::max(R0 - 6, 0)] - 1, 0), h - 1), S1 = src_hi(R1);
+    // device staging: tight rows, 256-byte aligned frames; only the rows this call needs
+    const size_t s_row = align_up((size_t)w * 3, 4), d_row = align_up((size_t)ow * 3, 4);
+    const size_t s_frame = align_up(s_row * (size_t)(S1 - S0), 256), d_frame = align_up(d_row * (size_t)(R1 - R0), 256);
+    // frames in flight are bounded so staging stays modest (<= ~1 GiB of output; one frame may be larger)
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n, ((size_t)1 << 30) / d_frame));
+    if ((rc = ensure(c, c->src_buf, s_frame * chunk))) return rc;
+    if ((rc = ensure(c, c->dst_buf, d_frame * chunk))) return rc;
+    uint8_t* ds = (uint8_t*)c->src_buf.p;
+    uint8_t* dd = (uint8_t*)c->dst_buf.p;
+    if (!c->s_in) {
+        SRCNN_CUDA(c, cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+        SRCNN_CUDA(c, cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+    }
+    auto event_at = [&](size_t i, cudaEvent_t* e) -> int {
+        while (c->pipe_events.size() <= i) {
+            cudaEvent_t ev;
+            SRCNN_CUDA(c, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            c->pipe_events.push_back(ev);
+        }
+        *e = c->pipe_events[i];
+        return SRCNN_OK;
+    };
+    // A single large frame is cut into sub-bands of >= 512 output rows (at most c->host_bands, default 8); each sub-band's
+    // source rows are copied in separately, so the first one computes after a fraction of the H2D and the D2H stream (the
+    // PCIe-bound leg) starts early and never idles.  Measured at 1080p -> 4K: 4 bands 0.587 ms, 8 bands 0.592 ms, 12 bands
+    // 0.72 ms (per-band launch overhead of the persistent kernel takes over).  Very tall bands (a gigapixel image) are cut
+    // so that a sub-band's planes stay below ~256 MB.
+    const int rows = R1 - R0;
+    int bands = 1;
+    if (n == 1 && rows >= 1024) {
+        bands = std::min(c->host_bands, rows / 512);
+        const long long by_mem = ((long long)rows * (long long)ow * 4 + (256ll << 20) - 1) / (256ll << 20);
+        bands = (int)std::max<long long>(bands, std::min<long long>(by_mem, rows / 64));
+    }
+    StreamDrain drain{c};
+    cudaEvent_t ev_start;
+    if ((rc = event_at(0, &ev_start))) return rc;
+    for (int f0 = 0; f0 < n; f0 += chunk) {
+        const int m = std::min(chunk, n - f0);
+        size_t ei = 1;
+        // everything queued earlier on the compute stream (previous calls, tap-table uploads) precedes the copies
+        SRCNN_CUDA(c, cudaEventRecord(ev_start, c->stream));
+        SRCNN_CUDA(c, cudaStreamWaitEvent(c->s_in, ev_start, 0));
+        SRCNN_CUDA(c, cudaStreamWaitEvent(c->s_out, ev_start, 0));
+        for (int f = 0; f < m; f++) {
+            const uint8_t* hsrc = src + (size_t)(f0 + f) * src_frame_stride;
+            uint8_t* hdst = dst + (size_t)(f0 + f) * dst_frame_stride;
+            int copied = S0;   // source rows [S0, copied) of this frame are on their way to the device
+            for (int bi = 0; bi < bands; bi++) {
+                const int r0 = R0 + (int)((long long)rows * bi / bands), r1 = R0 + (int)((long long)rows * (bi + 1) / bands);
+                const int s_hi = bi + 1 < bands ? src_hi(r1) : S1;
+                if (s_hi > copied) {
+                    cudaEvent_t ev_in;
+                    if ((rc = event_at(ei++, &ev_in))) return rc;
+                    SRCNN_CUDA(c, cudaMemcpy2DAsync(ds + f * s_frame + (size_t)(copied - S0) * s_row, s_row, hsrc + (size_t)copied * src_stride,
+                                                    src_stride, (size_t)w * 3, s_hi - copied, cudaMemcpyHostToDevice, c->s_in));
+                    SRCNN_CUDA(c, cudaEventRecord(ev_in, c->s_in));
+                    SRCNN_CUDA(c, cudaStreamWaitEvent(c->stream, ev_in, 0));
+                    copied = s_hi;
+                }
+                rc = process_rows(c, ds + f * s_frame, w, h, s_row, S0, S1, order, scale, ow, oh, r0, r1,
+                                  dd + f * d_frame + (size_t)(r0 - R0) * d_row, d_row);
+                if (rc) return rc;
+                cudaEvent_t ev_done;
+                if ((rc = event_at(ei++, &ev_done))) return rc;
+                SRCNN_CUDA(c, cudaEventRecord(ev_done, c->stream));
+                SRCNN_CUDA(c, cudaStreamWaitEvent(c->s_out, ev_done, 0));
+                SRCNN_CUDA(c, cudaMemcpy2DAsync(hdst + (size_t)(r0 - R0) * dst_stride, dst_stride,
+                                                dd + f * d_frame + (size_t)(r0 - R0) * d_row, d_row, (size_t)ow * 3, r1 - r0,
+                                                cudaMemcpyDeviceToHost, c->s_out));
+            }
+        }
+        SRCNN_CUDA(c, cudaStreamSynchronize(c->s_out));
+        SRCNN_CUDA(c, cudaStreamSynchronize(c->stream));
+        rc = check_guard(c);
+        if (rc) return rc;
+    }
+    return SRCNN_OK;
+}
+
 }  // namespace srcnn
 
 using namespace srcnn;
 
-#define ENTER(ctx)                                                                       \
-    if (!(ctx)) return SRCNN_E_ARG;                                                      \
-    do {                                                                                 \
-        cudaError_t e__ = cudaSetDevice((ctx)->device);                                  \
-        if (e__ != cudaSuccess) return fail((ctx), SRCNN_E_CUDA, "cudaSetDevice(%d): %s", (ctx)->device, cudaGetErrorString(e__)); \
+// Every entry point runs on the context's device and puts the caller's current device back on return (a host
+// application -- PyTorch, for one -- keeps its own notion of the current device).
+#define ENTER(ctx)                                                                                              \
+    if (!(ctx)) return SRCNN_E_ARG;                                                                             \
+    srcnn::DeviceScope dev_scope__((ctx)->device);                                                              \
+    if (!dev_scope__.ok) return fail((ctx), SRCNN_E_CUDA, "cudaSetDevice(%d) failed", (ctx)->device)
+// the whole-path calls also report a watchdog trip of an EARLIER launch (callers that synchronise through their own
+// stream never pass srcnn_sync)
+#define ENTER_PROCESS(ctx)                                                                                      \
+    ENTER(ctx);                                                                                                 \
+    do {                                                                                                        \
+        int g__ = check_guard(ctx);                                                                             \
+        if (g__) return g__;                                                                                    \
+        if ((ctx)->profiling) (ctx)->prof_calls++;                                                              \
     } while (0)
 
 extern "C" {
@@ -204,7 +333,8 @@ int srcnn_create(srcnn_ctx** out, int device, int variant) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SRCNN_E_NODEVICE;
     if (prop.major != 10) return SRCNN_E_NODEVICE;  // the only code in this library is sm_100a SASS
-    if (cudaSetDevice(device) != cudaSuccess) return SRCNN_E_NODEVICE;
+    srcnn::DeviceScope scope(device);
+    if (!scope.ok) return SRCNN_E_NODEVICE;
     srcnn_ctx* c = new (std::nothrow) srcnn_ctx();
     if (!c) return SRCNN_E_NOMEM;
     c->device = device;
@@ -218,27 +348,31 @@ int srcnn_create(srcnn_ctx** out, int device, int variant) {
     c->own_stream = true;
     if (srcnn_weights_blob_size != sizeof(float) * kNumParams) return bail(SRCNN_E_ARG);
     if (cudaMalloc(&c->d_params, sizeof(float) * kNumParams) != cudaSuccess) return bail(SRCNN_E_NOMEM);
-    if (cudaMemcpy(c->d_params, srcnn_weights_blob, sizeof(float) * kNumParams, cudaMemcpyHostToDevice) != cudaSuccess) return bail(SRCNN_E_CUDA);
+    if (cudaMemcpyAsync(c->d_params, srcnn_weights_blob, sizeof(float) * kNumParams, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) return bail(SRCNN_E_CUDA);
     if (cudaHostAlloc((void**)&c->h_guard, 128 * sizeof(int), cudaHostAllocMapped) != cudaSuccess) return bail(SRCNN_E_NOMEM);
     memset(c->h_guard, 0, 128 * sizeof(int));
     if (cudaHostGetDevicePointer((void**)&c->d_guard, c->h_guard, 0) != cudaSuccess) return bail(SRCNN_E_CUDA);
-    int rc = tc_prepare_weights(c, (const float*)srcnn_weights_blob);
+    int rc = fp32_prepare(c);
     if (rc) return bail(rc);
     rc = tc2_prepare_weights(c, (const float*)srcnn_weights_blob);
     if (rc) return bail(rc);
-    if (const char* k = getenv("SRCNN_TC_KERNEL")) c->tc_kernel = atoi(k) == 1 ? 1 : 2;
+    // every upload above came from pageable memory (the embedded blob, a std::vector): such a copy may return before its
+    // DMA has landed, and the context's non-blocking stream is not ordered against the legacy stream.  One device-wide
+    // synchronisation here and the first launch -- on whatever stream -- sees the parameters.
+    if (cudaDeviceSynchronize() != cudaSuccess) return bail(SRCNN_E_CUDA);
     if (const char* k = getenv("SRCNN_FUSE_MERGE")) c->fuse_merge = atoi(k) != 0;
     if (const char* k = getenv("SRCNN_TC2_SEG_OVH")) c->tc2_seg_ovh = std::max(0, std::min(64, atoi(k)));   // tuning aid
+    if (const char* k = getenv("SRCNN_HOST_BANDS")) c->host_bands = std::max(1, std::min(64, atoi(k)));     // tuning aid
     *out = c;
     return SRCNN_OK;
 }
 
 int srcnn_destroy(srcnn_ctx* c) {
     if (!c) return SRCNN_E_ARG;
-    cudaSetDevice(c->device);
+    srcnn::DeviceScope scope(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    tc_release(c);
     tc2_release(c);
+    fraw_release(c);
     for (auto& t : c->taps) {
         if (t.d_ofs) cudaFree(t.d_ofs);
         if (t.d_coef) cudaFree(t.d_coef);
@@ -249,7 +383,6 @@ int srcnn_destroy(srcnn_ctx* c) {
     for (cudaEvent_t e : c->pipe_events) cudaEventDestroy(e);
     if (c->s_in) cudaStreamDestroy(c->s_in);
     if (c->s_out) cudaStreamDestroy(c->s_out);
-    if (c->h_work) cudaFreeHost(c->h_work);
     if (c->d_params) cudaFree(c->d_params);
     if (c->h_guard) cudaFreeHost(c->h_guard);
     if (c->own) cudaStreamDestroy(c->own);
@@ -259,6 +392,7 @@ int srcnn_destroy(srcnn_ctx* c) {
 }
 
 const char* srcnn_last_error(srcnn_ctx* c) { return c ? c->err : "null context"; }
+int srcnn_last_failed_stage(srcnn_ctx* c) { return c ? c->fail_stage : SRCNN_E_ARG; }
 
 int srcnn_set_variant(srcnn_ctx* c, int variant) {
     if (!c || (variant != SRCNN_VARIANT_TC && variant != SRCNN_VARIANT_FP32)) return SRCNN_E_ARG;
@@ -266,13 +400,8 @@ int srcnn_set_variant(srcnn_ctx* c, int variant) {
     return SRCNN_OK;
 }
 int srcnn_get_variant(srcnn_ctx* c) { return c ? c->variant : SRCNN_E_ARG; }
+int srcnn_get_device(srcnn_ctx* c) { return c ? c->device : SRCNN_E_ARG; }
 
-// test hook (not part of the stable ABI): 2 = row-walking tcgen05 kernel (default), 1 = first-generation kernel
-extern "C" __attribute__((visibility("default"))) int srcnn_debug_set_tc_kernel(srcnn_ctx* c, int k) {
-    if (!c || (k != 1 && k != 2)) return SRCNN_E_ARG;
-    c->tc_kernel = k;
-    return SRCNN_OK;
-}
 // test hook: 1 = merge + colour-back fused into the tcgen05 kernel, 0 = separate K-C launch (default)
 extern "C" __attribute__((visibility("default"))) int srcnn_debug_set_fuse_merge(srcnn_ctx* c, int on) {
     if (!c) return SRCNN_E_ARG;
@@ -289,6 +418,11 @@ extern "C" __attribute__((visibility("default"))) int srcnn_debug_tc2_partition(
 extern "C" __attribute__((visibility("default"))) int srcnn_debug_set_tc2_seg_ovh(srcnn_ctx* c, int ovh) {
     if (!c || ovh < 0 || ovh > 64) return SRCNN_E_ARG;
     c->tc2_seg_ovh = ovh;
+    return SRCNN_OK;
+}
+extern "C" __attribute__((visibility("default"))) int srcnn_debug_set_host_bands(srcnn_ctx* c, int bands) {
+    if (!c || bands < 1 || bands > 64) return SRCNN_E_ARG;
+    c->host_bands = bands;
     return SRCNN_OK;
 }
 
@@ -315,11 +449,12 @@ int srcnn_profile_enable(srcnn_ctx* c, int on) {
     SRCNN_CUDA(c, cudaStreamSynchronize(c->stream));
     c->profiling = on != 0;
     c->ev_used = 0;
+    c->prof_calls = 0;
     return SRCNN_OK;
 }
 
-// Sums the device time of the three stages over every whole-path call since the last read:
-// ms[0] colour+bicubic, ms[1] fused SRCNN, ms[2] merge+colour-back; *calls = number of calls.
+// Sums the device time of the three stages over every band processed since the last read:
+// ms[0] colour+bicubic, ms[1] fused SRCNN, ms[2] merge+colour-back; *calls = number of whole-path API calls.
 int srcnn_profile_read(srcnn_ctx* c, double* ms, int* calls) {
     ENTER(c);
     if (!ms || !calls) return fail(c, SRCNN_E_ARG, "null pointer");
@@ -332,8 +467,9 @@ int srcnn_profile_read(srcnn_ctx* c, double* ms, int* calls) {
             SRCNN_CUDA(c, cudaEventElapsedTime(&t, c->ev_pool[4 * i + k], c->ev_pool[4 * i + k + 1]));
             ms[k] += t;
         }
-    *calls = (int)n;
+    *calls = c->prof_calls;
     c->ev_used = 0;
+    c->prof_calls = 0;
     return SRCNN_OK;
 }
 
@@ -347,7 +483,8 @@ int srcnn_out_dims(int w, int h, float scale, int* ow, int* oh) {
 
 int srcnn_host_alloc(void** p, size_t bytes) {
     if (!p) return SRCNN_E_ARG;
-    cudaError_t e = cudaHostAlloc(p, bytes, cudaHostAllocDefault);
+    // portable: page-locked for every device of the process (the multi-GPU driver copies from one buffer to all of them)
+    cudaError_t e = cudaHostAlloc(p, bytes, cudaHostAllocPortable);
     if (e != cudaSuccess) { cudaGetLastError(); *p = nullptr; return SRCNN_E_NOMEM; }
     return SRCNN_OK;
 }
@@ -355,10 +492,21 @@ int srcnn_host_free(void* p) {
     if (!p) return SRCNN_OK;
     return cudaFreeHost(p) == cudaSuccess ? SRCNN_OK : SRCNN_E_CUDA;
 }
+int srcnn_host_register(void* p, size_t bytes) {
+    if (!p || !bytes) return SRCNN_E_ARG;
+    cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) { cudaGetLastError(); return e == cudaErrorMemoryAllocation ? SRCNN_E_NOMEM : SRCNN_E_CUDA; }
+    return SRCNN_OK;
+}
+int srcnn_host_unregister(void* p) {
+    if (!p) return SRCNN_OK;
+    if (cudaHostUnregister(p) != cudaSuccess) { cudaGetLastError(); return SRCNN_E_CUDA; }
+    return SRCNN_OK;
+}
 
 int srcnn_process_device(srcnn_ctx* c, const uint8_t* d_src, int w, int h, size_t src_stride, int order, float scale,
                          uint8_t* d_dst, size_t dst_stride) {
-    ENTER(c);
+    ENTER_PROCESS(c);
     int ow, oh;
     int rc = check_image(c, d_src, w, h, src_stride, order, scale, d_dst, dst_stride, &ow, &oh);
     if (rc) return rc;
@@ -368,7 +516,7 @@ int srcnn_process_device(srcnn_ctx* c, const uint8_t* d_src, int w, int h, size_
 int srcnn_process_batch_device(srcnn_ctx* c, const uint8_t* d_src, int n, int w, int h, size_t src_stride,
                                size_t src_frame_stride, int order, float scale, uint8_t* d_dst, size_t dst_stride,
                                size_t dst_frame_stride) {
-    ENTER(c);
+    ENTER_PROCESS(c);
     if (n < 0) return fail(c, SRCNN_E_ARG, "negative frame count");
     if (n == 0) return SRCNN_OK;
     int ow, oh;
@@ -387,7 +535,7 @@ int srcnn_process_batch_device(srcnn_ctx* c, const uint8_t* d_src, int n, int w,
 int srcnn_process_batch_host(srcnn_ctx* c, const uint8_t* src, int n, int w, int h, size_t src_stride,
                              size_t src_frame_stride, int order, float scale, uint8_t* dst, size_t dst_stride,
                              size_t dst_frame_stride) {
-    ENTER(c);
+    ENTER_PROCESS(c);
     if (n < 0) return fail(c, SRCNN_E_ARG, "negative frame count");
     if (n == 0) return SRCNN_OK;
     int ow, oh;
@@ -395,88 +543,7 @@ int srcnn_process_batch_host(srcnn_ctx* c, const uint8_t* src, int n, int w, int
     if (rc) return rc;
     if (n > 1 && (src_frame_stride < src_stride * (size_t)h || dst_frame_stride < dst_stride * (size_t)oh))
         return fail(c, SRCNN_E_ARG, "frame stride smaller than one frame");
-    // device staging: tight rows, 256-byte aligned frames
-    const size_t s_row = align_up((size_t)w * 3, 4), d_row = align_up((size_t)ow * 3, 4);
-    const size_t s_frame = align_up(s_row * h, 256), d_frame = align_up(d_row * oh, 256);
-    // frames in flight are bounded so staging stays modest (<= ~1 GiB of output)
-    int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n, ((size_t)1 << 30) / d_frame));
-    rc = ensure(c, c->src_buf, s_frame * chunk);
-    if (rc) return rc;
-    rc = ensure(c, c->dst_buf, d_frame * chunk);
-    if (rc) return rc;
-    uint8_t* ds = (uint8_t*)c->src_buf.p;
-    uint8_t* dd = (uint8_t*)c->dst_buf.p;
-    // Three-stage pipeline on three streams: copy-in (H2D), compute (the context stream), copy-out (D2H).
-    // A unit is one row band of one frame (a single frame is cut into bands so that its D2H -- 4x the H2D
-    // bytes at x2 -- overlaps the kernels of the next band; frames of a batch overlap the same way).
-    if (!c->s_in) {
-        SRCNN_CUDA(c, cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
-        SRCNN_CUDA(c, cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
-    }
-    auto event_at = [&](size_t i, cudaEvent_t* e) -> int {
-        while (c->pipe_events.size() <= i) {
-            cudaEvent_t ev;
-            SRCNN_CUDA(c, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-            c->pipe_events.push_back(ev);
-        }
-        *e = c->pipe_events[i];
-        return SRCNN_OK;
-    };
-    // A single large frame is cut into up to 8 row bands of >= 512 output rows; each band's source rows (with the halo its
-    // taps need) are copied in separately, so the first band computes after a fraction of the H2D and the D2H stream (the
-    // PCIe-bound leg: 4x the H2D bytes at x2) starts early and never idles.  Measured at 1080p -> 4K: 4 bands 0.587 ms,
-    // 8 bands 0.592 ms, 12 bands 0.72 ms (per-band launch overhead of the persistent kernel takes over).
-    int max_bands = 8;
-    if (const char* e = getenv("SRCNN_HOST_BANDS")) max_bands = std::max(1, std::min(64, atoi(e)));   // tuning aid
-    const int bands = (n == 1 && oh >= 1024) ? std::min(max_bands, oh / 512) : 1;
-    TapTable* ty = nullptr;
-    if (bands > 1 && (rc = get_taps(c, h, oh, &ty))) return rc;
-    cudaEvent_t ev_start;
-    if ((rc = event_at(0, &ev_start))) return rc;
-    for (int f0 = 0; f0 < n; f0 += chunk) {
-        const int m = std::min(chunk, n - f0);
-        size_t ei = 1;
-        // everything queued earlier on the compute stream (previous calls, tap-table uploads) precedes the copies
-        SRCNN_CUDA(c, cudaEventRecord(ev_start, c->stream));
-        SRCNN_CUDA(c, cudaStreamWaitEvent(c->s_in, ev_start, 0));
-        SRCNN_CUDA(c, cudaStreamWaitEvent(c->s_out, ev_start, 0));
-        for (int f = 0; f < m; f++) {
-            const uint8_t* hsrc = src + (size_t)(f0 + f) * src_frame_stride;
-            int copied = 0;   // source rows [0, copied) of this frame are on their way to the device
-            for (int bi = 0; bi < bands; bi++) {
-                const int r0 = (int)((long long)oh * bi / bands), r1 = (int)((long long)oh * (bi + 1) / bands);
-                int s_hi = h;
-                if (bands > 1 && bi + 1 < bands) {   // last source row the band's bicubic taps touch (6-px halo in the output)
-                    const int p1 = std::min(r1 + 6, oh);
-                    s_hi = std::min(std::max(ty->h_ofs[p1 - 1] + 2, 0), h - 1) + 1;
-                }
-                if (s_hi > copied) {
-                    cudaEvent_t ev_in;
-                    if ((rc = event_at(ei++, &ev_in))) return rc;
-                    SRCNN_CUDA(c, cudaMemcpy2DAsync(ds + f * s_frame + (size_t)copied * s_row, s_row, hsrc + (size_t)copied * src_stride,
-                                                    src_stride, (size_t)w * 3, s_hi - copied, cudaMemcpyHostToDevice, c->s_in));
-                    SRCNN_CUDA(c, cudaEventRecord(ev_in, c->s_in));
-                    SRCNN_CUDA(c, cudaStreamWaitEvent(c->stream, ev_in, 0));
-                    copied = s_hi;
-                }
-                rc = process_rows(c, ds + f * s_frame, w, h, s_row, 0, h, order, scale, ow, oh, r0, r1,
-                                  dd + f * d_frame + (size_t)r0 * d_row, d_row);
-                if (rc) return rc;
-                cudaEvent_t ev_done;
-                if ((rc = event_at(ei++, &ev_done))) return rc;
-                SRCNN_CUDA(c, cudaEventRecord(ev_done, c->stream));
-                SRCNN_CUDA(c, cudaStreamWaitEvent(c->s_out, ev_done, 0));
-                SRCNN_CUDA(c, cudaMemcpy2DAsync(dst + (size_t)(f0 + f) * dst_frame_stride + (size_t)r0 * dst_stride, dst_stride,
-                                                dd + f * d_frame + (size_t)r0 * d_row, d_row, (size_t)ow * 3, r1 - r0,
-                                                cudaMemcpyDeviceToHost, c->s_out));
-            }
-        }
-        SRCNN_CUDA(c, cudaStreamSynchronize(c->s_out));
-        SRCNN_CUDA(c, cudaStreamSynchronize(c->stream));
-        rc = check_guard(c);
-        if (rc) return rc;
-    }
-    return SRCNN_OK;
+    return host_pipeline(c, src, n, w, h, src_stride, src_frame_stride, order, scale, ow, oh, 0, oh, dst, dst_stride, dst_frame_stride);
 }
 
 int srcnn_process_host(srcnn_ctx* c, const uint8_t* src, int w, int h, size_t src_stride, int order, float scale,
@@ -501,13 +568,23 @@ int srcnn_band_src_rows(int h, float scale, int r0, int r1, int* s0, int* s1) {
 
 int srcnn_process_band_device(srcnn_ctx* c, const uint8_t* d_src, int w, int h, size_t src_stride, int s0, int s1,
                               int order, float scale, int r0, int r1, uint8_t* d_dst, size_t dst_stride) {
-    ENTER(c);
+    ENTER_PROCESS(c);
     int ow, oh;
     int rc = check_image(c, d_src, w, h, src_stride, order, scale, d_dst, dst_stride, &ow, &oh);
     if (rc) return rc;
     if (r0 < 0 || r1 > oh || r0 >= r1) return fail(c, SRCNN_E_ARG, "bad output band [%d,%d) of %d rows", r0, r1, oh);
     if (s0 < 0 || s1 > h || s0 >= s1) return fail(c, SRCNN_E_ARG, "bad source band [%d,%d) of %d rows", s0, s1, h);
     return process_rows(c, d_src, w, h, src_stride, s0, s1, order, scale, ow, oh, r0, r1, d_dst, dst_stride);
+}
+
+int srcnn_process_band_host(srcnn_ctx* c, const uint8_t* src, int w, int h, size_t src_stride, int order, float scale,
+                            int r0, int r1, uint8_t* dst_rows, size_t dst_stride) {
+    ENTER_PROCESS(c);
+    int ow, oh;
+    int rc = check_image(c, src, w, h, src_stride, order, scale, dst_rows, dst_stride, &ow, &oh);
+    if (rc) return rc;
+    if (r0 < 0 || r1 > oh || r0 >= r1) return fail(c, SRCNN_E_ARG, "bad output band [%d,%d) of %d rows", r0, r1, oh);
+    return host_pipeline(c, src, 1, w, h, src_stride, 0, order, scale, ow, oh, r0, r1, dst_rows, dst_stride, 0);
 }
 
 int srcnn_stage_color_bicubic_device(srcnn_ctx* c, const uint8_t* d_src, int w, int h, size_t src_stride, int order,
@@ -534,6 +611,45 @@ int srcnn_stage_color_bicubic_device(srcnn_ctx* c, const uint8_t* d_src, int w, 
     ra.pl.pitch = plane_pitch; ra.pl.row0 = 0; ra.pl.rows = oh;
     ra.tx = tx; ra.ty = ty;
     return launch_color_bicubic(c, ra);
+}
+
+// One 8-bit plane through cv::resize(..., INTER_CUBIC) (src/srcnn.cpp:577-582), host buffers.  The colour+bicubic kernel
+// does it: a grey pixel (v,v,v) has Y = (16384 v + 8192) >> 14 = v, so its Y plane IS the resized plane.
+int srcnn_resize_plane_host(srcnn_ctx* c, const uint8_t* src, int w, int h, size_t src_stride, float scale, uint8_t* dst,
+                            size_t dst_stride) {
+    ENTER(c);
+    if (!src || !dst) return fail(c, SRCNN_E_ARG, "null pointer");
+    if (w <= 0 || h <= 0 || src_stride < (size_t)w) return fail(c, SRCNN_E_ARG, "bad source geometry");
+    if (!(((float)w * scale) > 0.f) || !(((float)h * scale) > 0.f)) return fail(c, SRCNN_E_RATIO, "ratio too small");
+    const int ow = scaled_dim(w, scale), oh = scaled_dim(h, scale);
+    if (ow <= 0 || oh <= 0) return fail(c, SRCNN_E_RATIO, "ratio too small");
+    if (dst_stride < (size_t)ow) return fail(c, SRCNN_E_ARG, "destination stride %zu < ow", dst_stride);
+    std::vector<uint8_t> grey;
+    try { grey.resize((size_t)w * h * 3); } catch (...) { return fail(c, SRCNN_E_NOMEM, "host staging"); }
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            const uint8_t v = src[(size_t)y * src_stride + x];
+            uint8_t* q = &grey[((size_t)y * w + x) * 3];
+            q[0] = q[1] = q[2] = v;
+        }
+    int rc = ensure(c, c->src_buf, grey.size());
+    if (rc) return rc;
+    Planes pl;
+    if ((rc = carve_planes(c, ow, oh, 0, &pl))) return rc;
+    TapTable *tx, *ty;
+    if ((rc = get_taps(c, w, ow, &tx))) return rc;
+    if ((rc = get_taps(c, h, oh, &ty))) return rc;
+    SRCNN_CUDA(c, cudaMemcpyAsync(c->src_buf.p, grey.data(), grey.size(), cudaMemcpyHostToDevice, c->stream));
+    ResizeArgs ra;
+    ra.src = (const uint8_t*)c->src_buf.p; ra.src_stride = (size_t)w * 3;
+    ra.sw = w; ra.sh = h; ra.src_row0 = 0; ra.src_row1 = h;
+    ra.order = SRCNN_ORDER_BGR; ra.ow = ow; ra.oh = oh;
+    ra.row_begin = 0; ra.row_end = oh;
+    ra.pl = pl; ra.tx = tx; ra.ty = ty;
+    if ((rc = launch_color_bicubic(c, ra))) return rc;
+    SRCNN_CUDA(c, cudaMemcpy2DAsync(dst, dst_stride, pl.y, pl.pitch, (size_t)ow, oh, cudaMemcpyDeviceToHost, c->stream));
+    SRCNN_CUDA(c, cudaStreamSynchronize(c->stream));
+    return SRCNN_OK;
 }
 
 int srcnn_stage_cnn_device(srcnn_ctx* c, int variant, const uint8_t* d_y, int w, int h, size_t pitch, uint8_t* d_out,

@@ -24,6 +24,20 @@ int fail(Ctx* c, int status, const char* fmt, ...);
                                "%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); \
     } while (0)
 
+// ---- the calling thread's current device is put back when an entry point returns ------------------
+struct DeviceScope {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceScope(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+        if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+        else prev = -1;   // nothing to restore
+    }
+    ~DeviceScope() { if (prev >= 0) cudaSetDevice(prev); }
+    DeviceScope(const DeviceScope&) = delete;
+    DeviceScope& operator=(const DeviceScope&) = delete;
+};
+
 // ---- a grow-only device buffer --------------------------------------------------------------------
 struct DevBuf {
     void* p = nullptr;
@@ -53,8 +67,6 @@ struct Planes {
     int row0 = 0, rows = 0;
 };
 
-struct TcWeights;  // srcnn_tc.cu
-
 // row-walking kernel: the cached cut of a launch's row steps over its pipelines (srcnn_tc2.cu, tc2_partition)
 struct Tc2Partition {
     int nstrips = 0, hb = 0, nworkers = 0, ovh = -1;
@@ -73,14 +85,13 @@ struct Ctx {
     char err[1536] = {0};
 
     float* d_params = nullptr;       // the 8129 fp32 parameters (FP32 variant reads these)
-    void* d_tc_weights = nullptr;    // packed FP16 operand images for the tcgen05 kernel
-    size_t tc_weights_bytes = 0;
-    void* d_tc2_weights = nullptr;   // same for the row-walking kernel (srcnn_tc2.cu)
+    float b3 = 0.f;                  // conv3 bias, handed to the fused kernel as a launch parameter
+    void* d_tc2_weights = nullptr;   // packed FP16 operand images for the row-walking tcgen05 kernel (srcnn_tc2.cu)
     bool fuse_merge = false;         // row-walking kernel: merge + YCrCb->BGR in its last epilogue instead of the K-C launch
                                      // (SRCNN_FUSE_MERGE=1; byte-identical, but 0.236 vs 0.214 ms per 4K frame: off by default)
     Tc2Partition tc2_part;
+    int host_bands = 8;              // host-buffer pipeline: most sub-bands a single frame is cut into (SRCNN_HOST_BANDS)
     int tc2_seg_ovh = 12;            // cost of opening a segment, in row steps (SRCNN_TC2_SEG_OVH; 0 = cut into equal row counts)
-    int tc_kernel = 2;               // 2 = row-walking kernel (default), 1 = first-generation kernel (SRCNN_TC_KERNEL=1)
     int* d_guard = nullptr;          // device-side watchdog flag (mapped pinned)
     int* h_guard = nullptr;
 
@@ -88,21 +99,22 @@ struct Ctx {
     DevBuf act2_buf;    // FP32 variant: conv2 activations (32 float planes) of one row chunk
     DevBuf src_buf;     // device copy of a host source image / batch
     DevBuf dst_buf;     // device copy of the result before D2H
-    DevBuf work_buf;    // TC kernel work list
-    void* h_work = nullptr;          // pinned staging for the work list
-    size_t h_work_cap = 0;
+    DevBuf work_buf;    // debug timeline of the fused kernel (SRCNN_TC_DEBUG=1)
 
     TapTable taps[8];
     unsigned long long tap_clock = 0;
+    void* fraw_cache = nullptr;      // fraw_resize.cu: contribution tables kept on the device per (filter, dst, src)
 
     // host-buffer pipeline (srcnn_process_batch_host): copy-in / copy-out streams and their events
     cudaStream_t s_in = nullptr, s_out = nullptr;
     std::vector<cudaEvent_t> pipe_events;
 
-    // optional per-stage device timing (srcnn_profile_*): 4 events per process call
+    // optional per-stage device timing (srcnn_profile_*): 4 events per band processed, prof_calls counts the API calls
     bool profiling = false;
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
+    int prof_calls = 0;
+    int fail_stage = 0;              // which stage the last failed whole-path call died in (srcnn_last_failed_stage)
 };
 int prof_mark(Ctx* c);   // records the next event of the pool on c->stream when profiling is on
 
@@ -160,9 +172,10 @@ struct CnnArgs {
     int order = 0;
 };
 int launch_cnn_fp32(Ctx* c, const CnnArgs& a, float* act2_out /* optional full act2 dump, may be null */);
-int launch_cnn_tc(Ctx* c, const CnnArgs& a);
-int tc_prepare_weights(Ctx* c, const float* params);
-void tc_release(Ctx* c);
+int fp32_prepare(Ctx* c);    // uploads the parameters to the device's constant bank (once per device and process)
+void fraw_release(Ctx* c);   // frees the cached frawscale contribution tables
+int host_pipeline(Ctx* c, const uint8_t* src, int n, int w, int h, size_t src_stride, size_t src_frame_stride, int order,
+                  float scale, int ow, int oh, int R0, int R1, uint8_t* dst, size_t dst_stride, size_t dst_frame_stride);
 int launch_cnn_tc2(Ctx* c, const CnnArgs& a);
 int tc2_prepare_weights(Ctx* c, const float* params);
 void tc2_release(Ctx* c);

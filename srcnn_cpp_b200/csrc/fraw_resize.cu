@@ -48,45 +48,49 @@ struct FrawFilter {
     }
 };
 
-// host restatement of FRawScaleWeightsTable::FRawScaleWeightsTable (src/frawscale.cpp:8-112)
+// Contribution table of one axis: for every destination sample the first source index, the number of taps and the
+// (renormalised) weights.  Same numbers, computed in the same order in double, as FRawScaleWeightsTable's constructor
+// (src/frawscale.cpp:8-112) -- bit-identical tables are what makes the resize bit-identical.
 struct FrawTable {
     int window = 0;
     std::vector<int> left, count;     // first source index and number of taps per destination sample
     std::vector<double> w;            // [dst][window + 1]
     FrawTable(const FrawFilter& f, unsigned dst, unsigned src) {
-        double dWidth, dFScale = 1.0;
-        const double dScale = double(dst) / double(src);
-        if (dScale < 1.0) { dWidth = f.width / dScale; dFScale = dScale; } else { dWidth = f.width; }
-        window = 2 * (int)ceil(dWidth) + 1;
+        const double ratio = double(dst) / double(src);
+        // down-scaling stretches the filter's support by 1/ratio and scales its argument by ratio (:21-33)
+        const double support = ratio < 1.0 ? f.width / ratio : f.width;
+        const double arg_scale = ratio < 1.0 ? ratio : 1.0;
+        window = 2 * (int)ceil(support) + 1;
         const int stride = window + 1;
         left.resize(dst); count.resize(dst); w.assign((size_t)dst * stride, 0.0);
-        const double dOffset = (0.5 / dScale) - 0.5;
+        const double shift = (0.5 / ratio) - 0.5;                        // centre of destination sample 0 in source units
+        const int last_src = int(src) - 1;
         for (unsigned u = 0; u < dst; u++) {
-            const double dCenter = (double)u / dScale + dOffset;
-            int iLeft = std::max(0, (int)floor(dCenter - dWidth));
-            int iRight = std::min((int)ceil(dCenter + dWidth), int(src) - 1);
-            if ((iRight - iLeft + 1) > window) {
-                if (iLeft < (int(src) - 1 / 2)) iLeft++; else iRight--;   // integer 1/2 == 0, as written at :57
+            const double centre = (double)u / ratio + shift;
+            int first = std::max(0, (int)floor(centre - support));      // borders are TRUNCATED, not replicated
+            int last = std::min((int)ceil(centre + support), last_src);
+            if (last - first + 1 > window) {
+                // the reference compares against `int(uSrcSize) - 1 / 2`, i.e. src - 0 (integer division), at :57:
+                // always true for a valid index, so it is always the left end that gives way
+                if (first < int(src) - 1 / 2) first++; else last--;
             }
             double* wt = &w[(size_t)u * stride];
             double total = 0;
-            for (int i = iLeft; i <= iRight; i++) {
-                const double weight = dFScale * f.eval(dFScale * (dCenter - (double)i));
-                wt[i - iLeft] = weight;
+            for (int i = first; i <= last; i++) {
+                const double weight = arg_scale * f.eval(arg_scale * (centre - (double)i));
+                wt[i - first] = weight;
                 total += weight;
             }
-            int right = iRight;
+            int kept_last = last;
             if (total > 0 && total != 1) {
-                for (int i = iLeft; i <= iRight; i++) wt[i - iLeft] /= total;
-                int k = iRight - iLeft;
-                while (wt[k] == 0) {                                   // :97-106 trims trailing zero taps
-                    right--;
-                    k--;
-                    if (right == iLeft) break;
+                for (int i = first; i <= last; i++) wt[i - first] /= total;
+                for (int k = last - first; wt[k] == 0; k--) {           // :97-106 drops trailing zero taps
+                    kept_last--;
+                    if (kept_last == first) break;
                 }
             }
-            left[u] = iLeft;
-            count[u] = right - iLeft + 1;
+            left[u] = first;
+            count[u] = kept_last - first + 1;
         }
     }
 };
@@ -120,54 +124,84 @@ __global__ void __launch_bounds__(256) k_fraw_horizontal(const float* __restrict
     dst[(size_t)y * dst_w + x] = (float)gray;
 }
 
+// Device copies of the tables, kept per context and (filter, dst, src): a stream of same-sized frames builds and uploads
+// them once, and no pass waits for the stream (an evicted entry is freed only after the stream has drained).
 struct DevTable {
+    int filter = -1;
+    unsigned dst = 0, src = 0;
     int* left = nullptr;
     int* count = nullptr;
     double* w = nullptr;
     int stride = 0;
-    void release() { cudaFree(left); cudaFree(count); cudaFree(w); }
+    unsigned long long stamp = 0;
+    void release() { cudaFree(left); cudaFree(count); cudaFree(w); left = count = nullptr; w = nullptr; filter = -1; }
+};
+struct FrawCache {
+    DevTable slot[8];
+    unsigned long long clock = 0;
 };
 
-int upload(Ctx* c, const FrawTable& t, DevTable* d) {
+int get_table(Ctx* c, const FrawFilter& f, unsigned dst, unsigned src, DevTable** out) {
+    if (!c->fraw_cache) c->fraw_cache = new FrawCache();
+    FrawCache* fc = (FrawCache*)c->fraw_cache;
+    DevTable* victim = &fc->slot[0];
+    for (auto& d : fc->slot) {
+        if (d.filter == f.kind && d.dst == dst && d.src == src) { d.stamp = ++fc->clock; *out = &d; return SRCNN_OK; }
+        if (d.stamp < victim->stamp) victim = &d;
+    }
+    DevTable* d = victim;
+    if (d->filter >= 0) {   // in-flight kernels may still read it
+        SRCNN_CUDA(c, cudaStreamSynchronize(c->stream));
+        d->release();
+    }
+    const FrawTable t(f, dst, src);
     d->stride = t.window + 1;
     SRCNN_CUDA(c, cudaMalloc(&d->left, sizeof(int) * t.left.size()));
     SRCNN_CUDA(c, cudaMalloc(&d->count, sizeof(int) * t.count.size()));
     SRCNN_CUDA(c, cudaMalloc(&d->w, sizeof(double) * t.w.size()));
+    // pageable sources: the runtime has staged them when the calls return, the vectors may go out of scope
     SRCNN_CUDA(c, cudaMemcpyAsync(d->left, t.left.data(), sizeof(int) * t.left.size(), cudaMemcpyHostToDevice, c->stream));
     SRCNN_CUDA(c, cudaMemcpyAsync(d->count, t.count.data(), sizeof(int) * t.count.size(), cudaMemcpyHostToDevice, c->stream));
     SRCNN_CUDA(c, cudaMemcpyAsync(d->w, t.w.data(), sizeof(double) * t.w.size(), cudaMemcpyHostToDevice, c->stream));
+    d->filter = f.kind; d->dst = dst; d->src = src;
+    d->stamp = ++fc->clock;
+    *out = d;
     return SRCNN_OK;
 }
 
 int run_vertical(Ctx* c, const FrawFilter& f, const float* src, unsigned width, unsigned sh, float* dst, unsigned dh) {
-    FrawTable t(f, dh, sh);
-    DevTable d;
-    int rc = upload(c, t, &d);
+    DevTable* d;
+    int rc = get_table(c, f, dh, sh, &d);
     if (rc) return rc;
     dim3 grid((width + 255) / 256, dh);
-    k_fraw_vertical<<<grid, 256, 0, c->stream>>>(src, width, dst, dh, d.left, d.count, d.w, d.stride);
+    k_fraw_vertical<<<grid, 256, 0, c->stream>>>(src, width, dst, dh, d->left, d->count, d->w, d->stride);
     c->launches++;
     SRCNN_CUDA(c, cudaGetLastError());
-    SRCNN_CUDA(c, cudaStreamSynchronize(c->stream));   // the tables are freed right away; this stage is not on the hot path
-    d.release();
     return SRCNN_OK;
 }
 
 int run_horizontal(Ctx* c, const FrawFilter& f, const float* src, unsigned sw, unsigned height, float* dst, unsigned dw) {
-    FrawTable t(f, dw, sw);
-    DevTable d;
-    int rc = upload(c, t, &d);
+    DevTable* d;
+    int rc = get_table(c, f, dw, sw, &d);
     if (rc) return rc;
     dim3 grid((dw + 255) / 256, height);
-    k_fraw_horizontal<<<grid, 256, 0, c->stream>>>(src, sw, dst, dw, height, d.left, d.count, d.w, d.stride);
+    k_fraw_horizontal<<<grid, 256, 0, c->stream>>>(src, sw, dst, dw, height, d->left, d->count, d->w, d->stride);
     c->launches++;
     SRCNN_CUDA(c, cudaGetLastError());
-    SRCNN_CUDA(c, cudaStreamSynchronize(c->stream));
-    d.release();
     return SRCNN_OK;
 }
 
 }  // namespace
+
+void fraw_release(Ctx* c) {
+    FrawCache* fc = (FrawCache*)c->fraw_cache;
+    if (!fc) return;
+    for (auto& d : fc->slot)
+        if (d.filter >= 0) d.release();
+    delete fc;
+    c->fraw_cache = nullptr;
+}
+
 }  // namespace srcnn
 
 using namespace srcnn;
@@ -175,7 +209,8 @@ using namespace srcnn;
 extern "C" int srcnn_fraw_scale_device(srcnn_ctx* c, const float* d_src, unsigned sw, unsigned sh, unsigned dw, unsigned dh,
                                        float* d_dst, int filter) {
     if (!c) return SRCNN_E_ARG;
-    if (cudaSetDevice(c->device) != cudaSuccess) return fail(c, SRCNN_E_CUDA, "cudaSetDevice failed");
+    srcnn::DeviceScope scope(c->device);
+    if (!scope.ok) return fail(c, SRCNN_E_CUDA, "cudaSetDevice failed");
     if (!d_src || !d_dst) return fail(c, SRCNN_E_ARG, "null pointer");
     if (sw == 0 || sh == 0 || dw == 0 || dh == 0) return fail(c, SRCNN_E_ARG, "empty plane");      // :168-169
     if (filter < 0 || filter > 2) return fail(c, SRCNN_E_ARG, "unknown filter %d", filter);

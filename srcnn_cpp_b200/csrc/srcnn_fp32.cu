@@ -13,12 +13,13 @@
 //
 // This variant is the parity yardstick for the tcgen05 kernel; it is CUDA-core bound (~14.5 k
 // non-fused FP32 ops per pixel) and materialises conv2's activations (128 B/px) in HBM in row chunks.
+#include <mutex>
+
 #include "common.h"
 
 namespace srcnn {
 
 __constant__ float c_params[kNumParams];
-static int g_const_loaded_dev = -1;
 
 __device__ __forceinline__ int clampi32(int v, int lo, int hi) { return min(max(v, lo), hi); }
 
@@ -105,16 +106,22 @@ __global__ void __launch_bounds__(256) k_conv55_strict(const float* __restrict__
     out[(size_t)(row - orow0) * out_pitch + col] = (uint8_t)t; // :240
 }
 
-static int load_constants(Ctx* c) {
-    if (g_const_loaded_dev == c->device) return SRCNN_OK;
-    SRCNN_CUDA(c, cudaMemcpyToSymbol(c_params, srcnn_weights_blob, sizeof(float) * kNumParams));
-    g_const_loaded_dev = c->device;
+// The parameters live in the constant bank of each DEVICE (one copy per device and process, shared by every context on it).
+// Called from srcnn_create with the context's device current; srcnn_create synchronises the device afterwards, so no
+// launch -- from this context or from one created later by another thread -- can run ahead of the upload.
+int fp32_prepare(Ctx* c) {
+    static std::mutex mu;
+    static bool loaded[64] = {false};
+    std::lock_guard<std::mutex> lock(mu);
+    if (c->device < 64 && loaded[c->device]) return SRCNN_OK;
+    SRCNN_CUDA(c, cudaMemcpyToSymbolAsync(c_params, srcnn_weights_blob, sizeof(float) * kNumParams, 0, cudaMemcpyHostToDevice, c->stream));
+    SRCNN_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->device < 64) loaded[c->device] = true;
     return SRCNN_OK;
 }
 
 int launch_cnn_fp32(Ctx* c, const CnnArgs& a, float* act2_out) {
-    int rc = load_constants(c);
-    if (rc) return rc;
+    int rc;
     const int W = a.W, H = a.H;
     if (act2_out) {  // full-image activations dump (stage API): plane stride H*W, row 0 = image row 0
         dim3 g1((W + kBX - 1) / kBX, (H + kBY - 1) / kBY);

@@ -79,12 +79,11 @@ constexpr int kBarsPerPipe = 9;                   // D1full[3] D2full[3] Tfull[3
 constexpr int kCtrBytes = 32;                     // per pipeline: freed[4] (T rows consumed, one per E3 warp), c1done, pad
 constexpr int kOffCtr = (kOffBar + 8 + 2 * kBarsPerPipe * 8 + 15) / 16 * 16;   // 16-byte aligned: freed[4] is read with one 128-bit load
 constexpr int kOffTmem = kOffCtr + 2 * kCtrBytes;
+constexpr int kOffWd = kOffTmem + 8;               // the launch's watchdog deadline (absolute %globaltimer value, u64)
 constexpr int kSmemBytes = kOffTmem + 64;
 constexpr int kThreads = 1024;                    // 2 pipelines x (E1, producer, E3, E2) warpgroups
 constexpr int kMaxWorkers = 2 * 152;              // pipelines of one launch (B200: 148 SMs); their ranges travel in the kernel parameters
 static_assert(kWeightBytes % 64 == 0 && kSmemBytes <= 227 * 1024, "shared memory budget");
-
-__constant__ float c_b3;
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -129,14 +128,26 @@ __device__ __noinline__ void watchdog_die(int* guard, int code) {
     __threadfence_system();
     __trap();
 }
-// bounded wait: a protocol bug must surface as an error code, never as a hung GPU.
+// Bounded waits: a protocol bug must surface as an error code, never as a hung GPU.  The bound is TIME, not a poll count
+// (a legitimate wait under a sanitizer, a profiler or heavy co-tenancy may take any number of polls, and a trap poisons the
+// whole process's CUDA context): the launch carries a deadline -- 4 s plus 1 ms per row step of the longest pipeline,
+// three orders of magnitude above the real run time; SRCNN_WATCHDOG_MS overrides it, 0 switches it off -- which thread 0
+// turns into an absolute %globaltimer value in shared memory.  A wait looks at the clock every 64 Ki polls; the check is
+// inline and stateless (a helper that RETURNS would make ptxas save the caller's registers around the call: stack frame,
+// spills), only the failure path is out of line.
+__device__ __forceinline__ void watchdog_look(uint32_t wd, int* guard, int code) {
+    unsigned long long now, deadline;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(deadline) : "r"(wd));
+    if (now > deadline) watchdog_die(guard, code);
+}
 // Plain try_wait: the hardware parks the warp until the phase completes or its own time limit passes (no issue slots
 // used meanwhile).  The suspend-time-hint form compiles to a NANOSLEEP.SYNCS loop that wakes on EVERY barrier event of
 // the CTA: ncu counted 18 wake-ups per wait, 28 % of all executed instructions, in the highest-priority warps.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* guard, int code) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t wd, int* guard, int code) {
     uint32_t tries = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++tries > (1u << 24)) watchdog_die(guard, code);   // seconds: >> any legitimate wait
+        if ((++tries & 0xFFFFu) == 0u) watchdog_look(wd, guard, code);
     }
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -166,28 +177,28 @@ __device__ __forceinline__ void warp_arrive(uint32_t bar, uint32_t leader) {
 __device__ __forceinline__ void ctr_publish(uint32_t addr, uint32_t v) {
     asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
-__device__ __forceinline__ void ctr_wait_ge(uint32_t addr, uint32_t need, int* guard, int code) {
+__device__ __forceinline__ void ctr_wait_ge(uint32_t addr, uint32_t need, uint32_t wd, int* guard, int code) {
     uint32_t v, tries = 0;
     for (;;) {
         asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
         if ((int)(v - need) >= 0) return;
-        if (++tries > (1u << 26)) watchdog_die(guard, code);
+        if ((++tries & 0xFFFFu) == 0u) watchdog_look(wd, guard, code);
     }
 }
-__device__ __forceinline__ void ctr_wait_ge4(uint32_t addr, uint32_t need, int* guard, int code) {   // min of four counters
+__device__ __forceinline__ void ctr_wait_ge4(uint32_t addr, uint32_t need, uint32_t wd, int* guard, int code) {   // min of four counters
     uint32_t a, b, c, d, tries = 0;
     for (;;) {
         asm volatile("ld.acquire.cta.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr) : "memory");
         if ((int)(a - need) >= 0 && (int)(b - need) >= 0 && (int)(c - need) >= 0 && (int)(d - need) >= 0) return;
-        if (++tries > (1u << 26)) watchdog_die(guard, code);
+        if ((++tries & 0xFFFFu) == 0u) watchdog_look(wd, guard, code);
     }
 }
 // A warpgroup waits for a tcgen05.commit: ONE warp polls the mbarrier, the other three park in a hardware named barrier
 // (no issue slots).  A parked try_wait returns every ~50 cycles; with all four warps of three roles polling, the polls
 // were 38 % of all executed instructions.
-__device__ __forceinline__ void wg_wait(uint32_t bar, uint32_t parity, bool poller, int barid, int* guard, int code) {
+__device__ __forceinline__ void wg_wait(uint32_t bar, uint32_t parity, bool poller, int barid, uint32_t wd, int* guard, int code) {
     if (poller) {
-        mbar_wait(bar, parity, guard, code);
+        mbar_wait(bar, parity, wd, guard, code);
         tc_fence_after();
         tc_fence_before();
     }
@@ -304,9 +315,11 @@ struct Params {
     size_t bgr_stride;
     int swap_rb;           // 1: R,G,B byte order
     const uint8_t* wimg;   // packed FP16 operand image (kWeightBytes)
+    float b3;              // conv3 bias (src/convdata.h:979), added in FP32 by the last epilogue
     long long total;       // strips x (out_end - out_begin) row steps
     long long bounds[kMaxWorkers + 1];   // pipeline w walks row steps [bounds[w], bounds[w+1]) of the strip-major order (tc2_partition)
     int* guard;
+    unsigned long long watchdog_ns;   // time allowance of this launch (0 = no deadline)
     long long* dbg;        // optional timeline (SRCNN_TC_DEBUG=1): clock64 stamps of pipeline 0 of CTA 0, first segment
 };
 constexpr int kDbgRows = 64, kDbgSlots = 8;
@@ -379,7 +392,7 @@ __device__ __forceinline__ void e3_step(const E3Ctx& c, const uint32_t (&hx_r)[5
     uint32_t tv[25];   // the 25 taps: three loads (16 + 8 + 1 columns) instead of one 32-register block
     TL2(2, rho - c.ta, 0);
     if (has_t) {
-        wg_wait(c.bars + 48 + uc.u * 8, uc.par, c.poller, 10 + pipe, p.guard, 40);   // TFULL
+        wg_wait(c.bars + 48 + uc.u * 8, uc.par, c.poller, 10 + pipe, c.bars + (kOffWd - kOffBar - 8) - pipe * (kBarsPerPipe * 8), p.guard, 40);   // TFULL
         TL2(2, rho - c.ta, 1);
         const uint32_t t = c.tml + uc.u * kUnitCols;
         tmem_ld16(t, tv);     // in flight while the previous row is stored
@@ -433,7 +446,7 @@ __device__ __forceinline__ void e3_step(const E3Ctx& c, const uint32_t (&hx_r)[5
         float sum = v[0];
 #pragma unroll
         for (int n = 1; n < 5; n++) sum += v[n];
-        sum += c_b3;                                // src/srcnn.cpp:235
+        sum += p.b3;                                // src/srcnn.cpp:235
         int q = (int)sum;                           // :238 truncation toward zero
         q = min(max(q, 0), 255);
         if constexpr (FUSED) {
@@ -505,7 +518,8 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
     // landing on sub-partition 0.
     const bool warp0 = (tp >> 5) == ((ROLE == 1 ? 0 : 2) + pipe);
     const uint32_t leader = elect_one();
-    if (ROLE != 2 && warp0) mbar_wait(wbar, 0, p.guard, 1);   // packed operands have landed in shared memory
+    const uint32_t wd = sbase + kOffWd;
+    if (ROLE != 2 && warp0) mbar_wait(wbar, 0, wd, p.guard, 1);   // packed operands have landed in shared memory
 
     while (lin < lin_end) {
         // ---- one segment: strip `strip`, output rows [ra, rb) ----
@@ -527,7 +541,7 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
             for (int i = 0; i < nT; i++) {
                 const uint32_t un = tml + uc.u * kUnitCols;
                 TL2(0, i, 0);
-                wg_wait(D1FULL(uc.u), uc.par, warp0, 3 + pipe, p.guard, 20);
+                wg_wait(D1FULL(uc.u), uc.par, warp0, 3 + pipe, wd, p.guard, 20);
                 rows_done++;
                 if (warp0 && leader) ctr_publish(ctr + 16, rows_done);   // conv1 of rows_done rows complete: their oldest ring rows may go
                 TL2(0, i, 1);
@@ -571,7 +585,7 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
             for (int i = 0; i < nT; i++) {
                 const uint32_t un = tml + uc.u * kUnitCols;
                 TL2(3, i, 0);
-                wg_wait(D2FULL(uc.u), uc.par, warp0, 5 + pipe, p.guard, 21);
+                wg_wait(D2FULL(uc.u), uc.par, warp0, 5 + pipe, wd, p.guard, 21);
                 TL2(3, i, 1);
                 uint32_t va[32];
                 tmem_ld32(un + 32, va);
@@ -664,7 +678,7 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
                 if (warp0 && t + 1 >= kSlots) {  // row t+1 reuses the slot of row t+1-11, last read by conv1 of that row
                     // (normally the counter value read one row ago already says so: no poll on the serial chain)
                     const uint32_t need = gbase + (uint32_t)(t + 2 - kSlots);
-                    if ((int)(seen_c - need) < 0) ctr_wait_ge(ctr + 16, need, p.guard, 30);
+                    if ((int)(seen_c - need) < 0) ctr_wait_ge(ctr + 16, need, wd, p.guard, 30);
                 }
                 TL2(1, t, 4);
                 named_bar(ybar, 128);
@@ -673,7 +687,7 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
                     if (rows_done >= 3u) {   // E3 has read T of row g-3 (again: usually known from last row's look)
                         const uint32_t need = rows_done - 2u;
                         if ((int)(seen_f[0] - need) < 0 || (int)(seen_f[1] - need) < 0 || (int)(seen_f[2] - need) < 0 || (int)(seen_f[3] - need) < 0)
-                            ctr_wait_ge4(ctr, need, p.guard, 11);
+                            ctr_wait_ge4(ctr, need, wd, p.guard, 11);
                     }
                     tc_fence_after();
                     TL2(1, t, 6);
@@ -776,6 +790,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_srcnn_tc2(const Params p) {
 
     if (tid < 16) reinterpret_cast<volatile uint32_t*>(smem + kOffCtr)[tid] = 0u;   // progress counters
     if (tid == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        const unsigned long long deadline = p.watchdog_ns ? now + p.watchdog_ns : ~0ull;
+        asm volatile("st.shared.u64 [%0], %1;" ::"r"(sbase + kOffWd), "l"(deadline) : "memory");
         mbar_init(wbar, 1);
         for (int q = 0; q < 2; q++)
             for (int i = 0; i < kBarsPerPipe; i++)
@@ -877,8 +895,10 @@ int tc2_prepare_weights(Ctx* c, const float* P) {
                 put_h2(img.data(), kImgB3 + (size_t)ks * 1024 + (size_t)(k / 8) * 512 + (size_t)n * 16 + (k % 8) * 2,
                        n < 25 ? w3[(ks * 16 + k) * 25 + n] : 0.f);
     SRCNN_CUDA(c, cudaMalloc(&c->d_tc2_weights, kWeightBytes));
-    SRCNN_CUDA(c, cudaMemcpy(c->d_tc2_weights, img.data(), kWeightBytes, cudaMemcpyHostToDevice));
-    SRCNN_CUDA(c, cudaMemcpyToSymbol(tc2::c_b3, P + kOffB3, sizeof(float)));
+    // pageable source: the runtime has staged `img` when this returns; srcnn_create synchronises the device afterwards
+    SRCNN_CUDA(c, cudaMemcpyAsync(c->d_tc2_weights, img.data(), kWeightBytes, cudaMemcpyHostToDevice, c->stream));
+    SRCNN_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->b3 = P[kOffB3];
     SRCNN_CUDA(c, cudaFuncSetAttribute(tc2::k_srcnn_tc2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     SRCNN_CUDA(c, cudaFuncSetAttribute(tc2::k_srcnn_tc2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     SRCNN_CUDA(c, cudaFuncSetAttribute(tc2::k_srcnn_tc2<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
@@ -944,6 +964,7 @@ int launch_cnn_tc2(Ctx* c, const CnnArgs& a) {
     p.bgr = a.bgr; p.bgr_stride = a.bgr_stride;
     p.swap_rb = a.order == SRCNN_ORDER_RGB ? 1 : 0;
     p.wimg = (const uint8_t*)c->d_tc2_weights;
+    p.b3 = c->b3;
     const int nstrips = (a.W + kStripCols - 1) / kStripCols;
     p.total = (long long)nstrips * (a.out_end - a.out_begin);
     p.guard = c->d_guard;
@@ -968,6 +989,11 @@ int launch_cnn_tc2(Ctx* c, const CnnArgs& a) {
         }
         memcpy(p.bounds, pt.bounds.data(), sizeof(long long) * (2 * grid + 1));
     }
+    {   // watchdog allowance: 4 s + 1 ms per row step of the longest pipeline (a row step takes ~0.6 us)
+        const long long longest = (p.total + 2 * grid - 1) / (2 * grid) + 64;
+        p.watchdog_ns = 4000000000ull + 1000000ull * (unsigned long long)longest;
+        if (const char* e = getenv("SRCNN_WATCHDOG_MS")) p.watchdog_ns = 1000000ull * (unsigned long long)std::max(0ll, atoll(e));
+    }
     if (p.bgr) k_srcnn_tc2<false, true><<<grid, kThreads, kSmemBytes, c->stream>>>(p);
     else if (p.dbg) k_srcnn_tc2<true, false><<<grid, kThreads, kSmemBytes, c->stream>>>(p);
     else k_srcnn_tc2<false, false><<<grid, kThreads, kSmemBytes, c->stream>>>(p);
@@ -981,7 +1007,7 @@ int launch_cnn_tc2(Ctx* c, const CnnArgs& a) {
 // debug hook: copies the last launch's timeline (4 roles x 64 rows x 8 stamps) to the host
 extern "C" __attribute__((visibility("default"))) int srcnn_debug_tc2_timeline(srcnn_ctx* c, long long* out) {
     if (!c || !c->work_buf.p) return SRCNN_E_ARG;
-    cudaSetDevice(c->device);
+    srcnn::DeviceScope scope(c->device);
     cudaStreamSynchronize(c->stream);
     const size_t bytes = 4 * srcnn::tc2::kDbgRows * srcnn::tc2::kDbgSlots * sizeof(long long);
     return cudaMemcpy(out, c->work_buf.p, bytes, cudaMemcpyDeviceToHost) == cudaSuccess ? SRCNN_OK : SRCNN_E_CUDA;

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), "libsrcnn_b200.so does not export " + n
     assert sorted(S.ABI_SYMBOLS) == names
-    assert L.srcnn_abi_version() == 1
+    assert L.srcnn_abi_version() == 2
 
 
 def test_out_dims_truncation():

@@ -120,17 +120,6 @@ def test_cnn_tc_within_tolerance_uniform_noise(engine, oracle, h, w):
     _tc_check(engine, oracle, rng.integers(0, 256, (h, w), dtype=np.uint8))
 
 
-@pytest.mark.parametrize("h,w", [(130, 140), (64, 5), (300, 200)])
-def test_cnn_tc_first_generation_kernel(engine, oracle, h, w):
-    """The first-generation fused kernel (srcnn_tc.cu) stays selectable and inside the same tolerance."""
-    rng = np.random.default_rng(h * 1000 + w + 7)
-    engine.set_tc_kernel(1)
-    try:
-        _tc_check(engine, oracle, rng.integers(0, 256, (h, w), dtype=np.uint8))
-    finally:
-        engine.set_tc_kernel(2)
-
-
 def test_cnn_tc_repeatable(engine, oracle):
     """Same input twice -> identical bytes (no dependence on scheduling inside the persistent kernel)."""
     import torch
