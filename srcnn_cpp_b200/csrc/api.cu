@@ -30,6 +30,7 @@ int fail(Ctx* c, int status, const char* fmt, ...) {
 
 int ensure(Ctx* c, DevBuf& b, size_t bytes) {
     if (bytes <= b.cap) return SRCNN_OK;
+    drop_graphs(c);   // captured pipelines hold the old device addresses
     if (b.p) {
         SRCNN_CUDA(c, cudaStreamSynchronize(c->stream));
         SRCNN_CUDA(c, cudaFree(b.p));
@@ -77,13 +78,17 @@ static int check_image(Ctx* c, const void* src, int w, int h, size_t stride, int
 static int carve_planes(Ctx* c, int ow, int rows, int row0, Planes* pl) {
     const size_t pitch = align_up((size_t)ow, 128);
     const size_t plane = pitch * (size_t)rows;
-    int rc = ensure(c, c->plane_buf, plane * 4);
+    const size_t pitch16 = y16_pitch_bytes(ow);
+    const size_t plane16 = align_up(pitch16 * (size_t)rows + 512, 256);   // slack: the last row's last strip copy may run past the row
+    int rc = ensure(c, c->plane_buf, plane * 4 + plane16);
     if (rc) return rc;
     uint8_t* base = (uint8_t*)c->plane_buf.p;
     pl->y = base;
     pl->cr = base + plane;
     pl->cb = base + 2 * plane;
     pl->yout = base + 3 * plane;
+    pl->y16 = base + 4 * plane;
+    pl->pitch16 = pitch16;
     pl->pitch = pitch;
     pl->row0 = row0;
     pl->rows = rows;
@@ -124,6 +129,7 @@ static int process_rows_impl(Ctx* c, const uint8_t* d_src, int w, int h, size_t 
     ra.ow = ow; ra.oh = oh;
     ra.row_begin = p0; ra.row_end = p1;
     ra.pl = pl; ra.tx = tx; ra.ty = ty;
+    if (c->variant != SRCNN_VARIANT_TC) ra.pl.y16 = nullptr;      // the strict FP32 kernels read the u8 plane
     if ((rc = prof_mark(c))) return rc;
     rc = launch_color_bicubic(c, ra);
     if (rc) return rc;
@@ -132,6 +138,7 @@ static int process_rows_impl(Ctx* c, const uint8_t* d_src, int w, int h, size_t 
     c->fail_stage = SRCNN_STAGE_CNN;
     CnnArgs ca;
     ca.y = pl.y; ca.pitch = pl.pitch;
+    ca.y16 = pl.y16; ca.pitch16 = pl.pitch16;
     ca.W = ow; ca.H = oh;
     ca.row0 = p0; ca.rows = p1 - p0;
     ca.out_begin = r0; ca.out_end = r1;
@@ -188,18 +195,100 @@ static int check_guard(Ctx* c) {
 struct StreamDrain {   // on every exit path: no async copy may still reference the caller's buffers
     Ctx* c;
     ~StreamDrain() {
+        if (c->capturing) return;   // a capture is ended (and thrown away) by its owner; nothing has run yet
         if (c->s_in) cudaStreamSynchronize(c->s_in);
         if (c->s_out) cudaStreamSynchronize(c->s_out);
         cudaStreamSynchronize(c->stream);
     }
 };
 
+static bool is_pinned(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+void drop_graphs(Ctx* c) {
+    for (auto& g : c->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    c->graphs.clear();
+}
+
+// Enqueues the whole pipeline of one chunk of frames (f0 .. f0+m) on the three streams and joins the copy streams back
+// into the compute stream; does not wait.  Identical whether the streams are live or being captured into a CUDA graph.
+static int enqueue_chunk(Ctx* c, const uint8_t* src, int f0, int m, int w, int h, size_t src_stride, size_t src_frame_stride, int order,
+                         float scale, int ow, int oh, int R0, int R1, uint8_t* dst, size_t dst_stride, size_t dst_frame_stride,
+                         const TapTable* ty, int S0, int S1, int bands, size_t s_row, size_t d_row, size_t s_frame, size_t d_frame) {
+    int rc;
+    uint8_t* ds = (uint8_t*)c->src_buf.p;
+    uint8_t* dd = (uint8_t*)c->dst_buf.p;
+    auto event_at = [&](size_t i, cudaEvent_t* e) -> int {
+        while (c->pipe_events.size() <= i) {
+            cudaEvent_t ev;
+            SRCNN_CUDA(c, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            c->pipe_events.push_back(ev);
+        }
+        *e = c->pipe_events[i];
+        return SRCNN_OK;
+    };
+    auto src_hi = [&](int r1) {   // one past the last source row output rows < r1 touch (6-px halo in the output)
+        const int p1 = std::min(r1 + 6, oh);
+        return std::min(std::max(ty->h_ofs[p1 - 1] + 2, 0), h - 1) + 1;
+    };
+    const int rows = R1 - R0;
+    cudaEvent_t ev_start;
+    if ((rc = event_at(0, &ev_start))) return rc;
+    size_t ei = 1;
+    // everything queued earlier on the compute stream (previous calls, tap-table uploads) precedes the copies
+    SRCNN_CUDA(c, cudaEventRecord(ev_start, c->stream));
+    SRCNN_CUDA(c, cudaStreamWaitEvent(c->s_in, ev_start, 0));
+    SRCNN_CUDA(c, cudaStreamWaitEvent(c->s_out, ev_start, 0));
+    for (int f = 0; f < m; f++) {
+        const uint8_t* hsrc = src + (size_t)(f0 + f) * src_frame_stride;
+        uint8_t* hdst = dst + (size_t)(f0 + f) * dst_frame_stride;
+        int copied = S0;   // source rows [S0, copied) of this frame are on their way to the device
+        for (int bi = 0; bi < bands; bi++) {
+            const int r0 = R0 + (int)((long long)rows * bi / bands), r1 = R0 + (int)((long long)rows * (bi + 1) / bands);
+            const int s_hi = bi + 1 < bands ? src_hi(r1) : S1;
+            if (s_hi > copied) {
+                cudaEvent_t ev_in;
+                if ((rc = event_at(ei++, &ev_in))) return rc;
+                SRCNN_CUDA(c, cudaMemcpy2DAsync(ds + f * s_frame + (size_t)(copied - S0) * s_row, s_row, hsrc + (size_t)copied * src_stride,
+                                                src_stride, (size_t)w * 3, s_hi - copied, cudaMemcpyHostToDevice, c->s_in));
+                SRCNN_CUDA(c, cudaEventRecord(ev_in, c->s_in));
+                SRCNN_CUDA(c, cudaStreamWaitEvent(c->stream, ev_in, 0));
+                copied = s_hi;
+            }
+            rc = process_rows(c, ds + f * s_frame, w, h, s_row, S0, S1, order, scale, ow, oh, r0, r1,
+                              dd + f * d_frame + (size_t)(r0 - R0) * d_row, d_row);
+            if (rc) return rc;
+            cudaEvent_t ev_done;
+            if ((rc = event_at(ei++, &ev_done))) return rc;
+            SRCNN_CUDA(c, cudaEventRecord(ev_done, c->stream));
+            SRCNN_CUDA(c, cudaStreamWaitEvent(c->s_out, ev_done, 0));
+            SRCNN_CUDA(c, cudaMemcpy2DAsync(hdst + (size_t)(r0 - R0) * dst_stride, dst_stride,
+                                            dd + f * d_frame + (size_t)(r0 - R0) * d_row, d_row, (size_t)ow * 3, r1 - r0,
+                                            cudaMemcpyDeviceToHost, c->s_out));
+        }
+    }
+    // join: the compute stream ends after the last copy in either direction
+    cudaEvent_t ev_j1, ev_j2;
+    if ((rc = event_at(ei++, &ev_j1))) return rc;
+    if ((rc = event_at(ei++, &ev_j2))) return rc;
+    SRCNN_CUDA(c, cudaEventRecord(ev_j1, c->s_in));
+    SRCNN_CUDA(c, cudaEventRecord(ev_j2, c->s_out));
+    SRCNN_CUDA(c, cudaStreamWaitEvent(c->stream, ev_j1, 0));
+    SRCNN_CUDA(c, cudaStreamWaitEvent(c->stream, ev_j2, 0));
+    return SRCNN_OK;
+}
+
 int host_pipeline(Ctx* c, const uint8_t* src, int n, int w, int h, size_t src_stride, size_t src_frame_stride, int order,
                   float scale, int ow, int oh, int R0, int R1, uint8_t* dst, size_t dst_stride, size_t dst_frame_stride) {
     int rc;
-    TapTable* ty = nullptr;
+    TapTable *ty = nullptr, *tx = nullptr;
     if ((rc = get_taps(c, h, oh, &ty))) return rc;
-    auto src_hi = [&](int r1) {   // one past the last source row output rows < r1 touch (6-px halo in the output)
+    if ((rc = get_taps(c, w, ow, &tx))) return rc;      // uploaded here, not inside a graph capture
+    auto src_hi = [&](int r1) {
         const int p1 = std::min(r1 + 6, oh);
         return std::min(std::max(ty->h_ofs[p1 - 1] + 2, 0), h - 1) + 1;
     };
@@ -211,21 +300,10 @@ int host_pipeline(Ctx* c, const uint8_t* src, int n, int w, int h, size_t src_st
     const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n, ((size_t)1 << 30) / d_frame));
     if ((rc = ensure(c, c->src_buf, s_frame * chunk))) return rc;
     if ((rc = ensure(c, c->dst_buf, d_frame * chunk))) return rc;
-    uint8_t* ds = (uint8_t*)c->src_buf.p;
-    uint8_t* dd = (uint8_t*)c->dst_buf.p;
     if (!c->s_in) {
         SRCNN_CUDA(c, cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
         SRCNN_CUDA(c, cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
     }
-    auto event_at = [&](size_t i, cudaEvent_t* e) -> int {
-        while (c->pipe_events.size() <= i) {
-            cudaEvent_t ev;
-            SRCNN_CUDA(c, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-            c->pipe_events.push_back(ev);
-        }
-        *e = c->pipe_events[i];
-        return SRCNN_OK;
-    };
     // A single large frame is cut into sub-bands of >= 512 output rows (at most c->host_bands, default 8); each sub-band's
     // source rows are copied in separately, so the first one computes after a fraction of the H2D and the D2H stream (the
     // PCIe-bound leg) starts early and never idles.  Measured at 1080p -> 4K: 4 bands 0.587 ms, 8 bands 0.592 ms, 12 bands
@@ -238,45 +316,71 @@ int host_pipeline(Ctx* c, const uint8_t* src, int n, int w, int h, size_t src_st
         const long long by_mem = ((long long)rows * (long long)ow * 4 + (256ll << 20) - 1) / (256ll << 20);
         bands = (int)std::max<long long>(bands, std::min<long long>(by_mem, rows / 64));
     }
+    {   // the planes of the tallest sub-band, allocated before anything is enqueued or captured
+        Planes pl;
+        const int tallest = (rows + bands - 1) / bands + 12;
+        if ((rc = carve_planes(c, ow, std::min(tallest, oh), 0, &pl))) return rc;
+    }
+
+    // ---- CUDA-graph replay.  A call that repeats an earlier one exactly (same buffers, same geometry: a stream of frames through
+    // a pair of pinned buffers) is ~50 API calls of host work for ~0.5 ms of device work; the second time a call is seen its
+    // pipeline is captured into a graph, from then on it is one cudaGraphLaunch.  One-off calls never pay for instantiation.
+    PipeGraph* hit = nullptr;
+    const bool graphable = c->use_graphs && !c->profiling && chunk >= n && bands * n <= 256;
+    if (graphable) {
+        PipeKey key{src, dst, n, w, h, src_stride, src_frame_stride, order, scale, R0, R1, dst_stride, dst_frame_stride, c->variant,
+                    (int)c->fuse_merge, c->host_bands, 0, 0, c->tc2_seg_ovh, (void*)c->stream};
+        for (auto& g : c->graphs)
+            if (memcmp(&g.key, &key, sizeof(key)) == 0) hit = &g;
+        if (!hit) {
+            if (c->graphs.size() >= 8) {   // forget the least recently used
+                size_t v = 0;
+                for (size_t i = 1; i < c->graphs.size(); i++)
+                    if (c->graphs[i].stamp < c->graphs[v].stamp) v = i;
+                if (c->graphs[v].exec) cudaGraphExecDestroy(c->graphs[v].exec);
+                c->graphs.erase(c->graphs.begin() + v);
+            }
+            PipeGraph g;
+            memset(&g.key, 0, sizeof(g.key));
+            g.key = key;
+            c->graphs.push_back(g);          // first sighting: run it live below
+            hit = nullptr;
+        } else {
+            hit->stamp = ++c->graph_clock;
+        }
+    }
+    if (hit && !hit->exec && !hit->failed && is_pinned(src) && is_pinned(dst)) {
+        // second sighting: capture.  Nothing below allocates, uploads or synchronises (tables, staging and planes exist).
+        cudaGraph_t graph = nullptr;
+        cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
+        if (e == cudaSuccess) {
+            c->capturing = true;
+            rc = enqueue_chunk(c, src, 0, n, w, h, src_stride, src_frame_stride, order, scale, ow, oh, R0, R1, dst, dst_stride,
+                               dst_frame_stride, ty, S0, S1, bands, s_row, d_row, s_frame, d_frame);
+            e = cudaStreamEndCapture(c->stream, &graph);
+            c->capturing = false;
+            if (rc == SRCNN_OK && e == cudaSuccess && graph && cudaGraphInstantiate(&hit->exec, graph, 0) != cudaSuccess) hit->exec = nullptr;
+            if (graph) cudaGraphDestroy(graph);
+        }
+        cudaGetLastError();
+        if (!hit->exec) hit->failed = true;   // run live from now on
+    }
     StreamDrain drain{c};
-    cudaEvent_t ev_start;
-    if ((rc = event_at(0, &ev_start))) return rc;
+    if (hit && hit->exec) {
+        SRCNN_CUDA(c, cudaGraphLaunch(hit->exec, c->stream));
+        c->launches += hit->kernel_launches;
+        SRCNN_CUDA(c, cudaStreamSynchronize(c->stream));
+        return check_guard(c);
+    }
     for (int f0 = 0; f0 < n; f0 += chunk) {
         const int m = std::min(chunk, n - f0);
-        size_t ei = 1;
-        // everything queued earlier on the compute stream (previous calls, tap-table uploads) precedes the copies
-        SRCNN_CUDA(c, cudaEventRecord(ev_start, c->stream));
-        SRCNN_CUDA(c, cudaStreamWaitEvent(c->s_in, ev_start, 0));
-        SRCNN_CUDA(c, cudaStreamWaitEvent(c->s_out, ev_start, 0));
-        for (int f = 0; f < m; f++) {
-            const uint8_t* hsrc = src + (size_t)(f0 + f) * src_frame_stride;
-            uint8_t* hdst = dst + (size_t)(f0 + f) * dst_frame_stride;
-            int copied = S0;   // source rows [S0, copied) of this frame are on their way to the device
-            for (int bi = 0; bi < bands; bi++) {
-                const int r0 = R0 + (int)((long long)rows * bi / bands), r1 = R0 + (int)((long long)rows * (bi + 1) / bands);
-                const int s_hi = bi + 1 < bands ? src_hi(r1) : S1;
-                if (s_hi > copied) {
-                    cudaEvent_t ev_in;
-                    if ((rc = event_at(ei++, &ev_in))) return rc;
-                    SRCNN_CUDA(c, cudaMemcpy2DAsync(ds + f * s_frame + (size_t)(copied - S0) * s_row, s_row, hsrc + (size_t)copied * src_stride,
-                                                    src_stride, (size_t)w * 3, s_hi - copied, cudaMemcpyHostToDevice, c->s_in));
-                    SRCNN_CUDA(c, cudaEventRecord(ev_in, c->s_in));
-                    SRCNN_CUDA(c, cudaStreamWaitEvent(c->stream, ev_in, 0));
-                    copied = s_hi;
-                }
-                rc = process_rows(c, ds + f * s_frame, w, h, s_row, S0, S1, order, scale, ow, oh, r0, r1,
-                                  dd + f * d_frame + (size_t)(r0 - R0) * d_row, d_row);
-                if (rc) return rc;
-                cudaEvent_t ev_done;
-                if ((rc = event_at(ei++, &ev_done))) return rc;
-                SRCNN_CUDA(c, cudaEventRecord(ev_done, c->stream));
-                SRCNN_CUDA(c, cudaStreamWaitEvent(c->s_out, ev_done, 0));
-                SRCNN_CUDA(c, cudaMemcpy2DAsync(hdst + (size_t)(r0 - R0) * dst_stride, dst_stride,
-                                                dd + f * d_frame + (size_t)(r0 - R0) * d_row, d_row, (size_t)ow * 3, r1 - r0,
-                                                cudaMemcpyDeviceToHost, c->s_out));
-            }
-        }
-        SRCNN_CUDA(c, cudaStreamSynchronize(c->s_out));
+        const long long l0 = c->launches;
+        rc = enqueue_chunk(c, src, f0, m, w, h, src_stride, src_frame_stride, order, scale, ow, oh, R0, R1, dst, dst_stride,
+                           dst_frame_stride, ty, S0, S1, bands, s_row, d_row, s_frame, d_frame);
+        if (rc) return rc;
+        if (graphable && f0 == 0)
+            for (auto& g : c->graphs)
+                if (!g.exec && g.kernel_launches == 0) g.kernel_launches = c->launches - l0;   // what a replay of this call launches
         SRCNN_CUDA(c, cudaStreamSynchronize(c->stream));
         rc = check_guard(c);
         if (rc) return rc;
@@ -362,6 +466,7 @@ int srcnn_create(srcnn_ctx** out, int device, int variant) {
     if (cudaDeviceSynchronize() != cudaSuccess) return bail(SRCNN_E_CUDA);
     if (const char* k = getenv("SRCNN_FUSE_MERGE")) c->fuse_merge = atoi(k) != 0;
     if (const char* k = getenv("SRCNN_TC2_SEG_OVH")) c->tc2_seg_ovh = std::max(0, std::min(64, atoi(k)));   // tuning aid
+    if (const char* k = getenv("SRCNN_GRAPHS")) c->use_graphs = atoi(k) != 0;                                // A/B aid
     if (const char* k = getenv("SRCNN_HOST_BANDS")) c->host_bands = std::max(1, std::min(64, atoi(k)));     // tuning aid
     *out = c;
     return SRCNN_OK;
@@ -371,13 +476,14 @@ int srcnn_destroy(srcnn_ctx* c) {
     if (!c) return SRCNN_E_ARG;
     srcnn::DeviceScope scope(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    drop_graphs(c);
     tc2_release(c);
     fraw_release(c);
     for (auto& t : c->taps) {
         if (t.d_ofs) cudaFree(t.d_ofs);
         if (t.d_coef) cudaFree(t.d_coef);
     }
-    for (DevBuf* b : {&c->plane_buf, &c->act2_buf, &c->src_buf, &c->dst_buf, &c->work_buf})
+    for (DevBuf* b : {&c->plane_buf, &c->y16_buf, &c->act2_buf, &c->src_buf, &c->dst_buf, &c->work_buf})
         if (b->p) cudaFree(b->p);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     for (cudaEvent_t e : c->pipe_events) cudaEventDestroy(e);
@@ -425,10 +531,19 @@ extern "C" __attribute__((visibility("default"))) int srcnn_debug_set_host_bands
     c->host_bands = bands;
     return SRCNN_OK;
 }
+// test hook: CUDA-graph replay of repeated host-buffer calls on / off; returns the number of instantiated graphs
+extern "C" __attribute__((visibility("default"))) int srcnn_debug_graphs(srcnn_ctx* c, int on) {
+    if (!c) return SRCNN_E_ARG;
+    if (on >= 0) c->use_graphs = on != 0;
+    int n = 0;
+    for (auto& g : c->graphs) n += g.exec != nullptr;
+    return n;
+}
 
 int srcnn_set_stream(srcnn_ctx* c, void* s) {
     ENTER(c);
     SRCNN_CUDA(c, cudaStreamSynchronize(c->stream));
+    drop_graphs(c);
     if (s) { c->stream = (cudaStream_t)s; c->own_stream = false; }
     else { c->stream = c->own; c->own_stream = true; }
     return SRCNN_OK;
@@ -607,7 +722,7 @@ int srcnn_stage_color_bicubic_device(srcnn_ctx* c, const uint8_t* d_src, int w, 
     ra.sw = w; ra.sh = h; ra.src_row0 = 0; ra.src_row1 = h;
     ra.order = order; ra.ow = ow; ra.oh = oh;
     ra.row_begin = 0; ra.row_end = oh;
-    ra.pl.y = d_y; ra.pl.cr = d_cr; ra.pl.cb = d_cb; ra.pl.yout = nullptr;
+    ra.pl.y = d_y; ra.pl.cr = d_cr; ra.pl.cb = d_cb; ra.pl.yout = nullptr; ra.pl.y16 = nullptr;
     ra.pl.pitch = plane_pitch; ra.pl.row0 = 0; ra.pl.rows = oh;
     ra.tx = tx; ra.ty = ty;
     return launch_color_bicubic(c, ra);
@@ -646,6 +761,7 @@ int srcnn_resize_plane_host(srcnn_ctx* c, const uint8_t* src, int w, int h, size
     ra.order = SRCNN_ORDER_BGR; ra.ow = ow; ra.oh = oh;
     ra.row_begin = 0; ra.row_end = oh;
     ra.pl = pl; ra.tx = tx; ra.ty = ty;
+    ra.pl.y16 = nullptr;
     if ((rc = launch_color_bicubic(c, ra))) return rc;
     SRCNN_CUDA(c, cudaMemcpy2DAsync(dst, dst_stride, pl.y, pl.pitch, (size_t)ow, oh, cudaMemcpyDeviceToHost, c->stream));
     SRCNN_CUDA(c, cudaStreamSynchronize(c->stream));

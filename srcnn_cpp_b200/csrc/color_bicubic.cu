@@ -13,6 +13,8 @@
 // last (ow mod 8) columns.  Results are bit-identical to the oracle (tests/test_stage_parity.py).
 //
 // Algorithmic HBM bytes per output pixel: 3/s^2 (BGR read) + 3 (planes written); K-C: 3 + 3.
+#include <cuda_fp16.h>
+
 #include <cmath>
 #include <cstdarg>
 
@@ -61,7 +63,8 @@ int get_taps(Ctx* c, int src, int dst, TapTable** out) {
         if (t.stamp < victim->stamp) victim = &t;
     }
     TapTable& t = *victim;
-    if (t.d_ofs) {  // evict: in-flight kernels may still read it
+    if (t.d_ofs) {  // evict: in-flight kernels may still read it, captured pipelines hold its addresses
+        drop_graphs(c);
         SRCNN_CUDA(c, cudaStreamSynchronize(c->stream));
         cudaFree(t.d_ofs);
         cudaFree(t.d_coef);
@@ -75,6 +78,7 @@ int get_taps(Ctx* c, int src, int dst, TapTable** out) {
     build_cubic_taps(src, dst, t.h_ofs.data(), t.h_coef.data());
     SRCNN_CUDA(c, cudaMalloc(&t.d_ofs, sizeof(int) * (size_t)dst));
     SRCNN_CUDA(c, cudaMalloc(&t.d_coef, sizeof(short4) * (size_t)dst));
+
     // pageable source: the runtime stages it before returning, so the vectors may be reused freely
     SRCNN_CUDA(c, cudaMemcpyAsync(t.d_ofs, t.h_ofs.data(), sizeof(int) * (size_t)dst, cudaMemcpyHostToDevice, c->stream));
     SRCNN_CUDA(c, cudaMemcpyAsync(t.d_coef, t.h_coef.data(), sizeof(short4) * (size_t)dst, cudaMemcpyHostToDevice, c->stream));
@@ -125,6 +129,8 @@ struct ResizeDev {
     uint8_t* cr;
     uint8_t* cb;
     size_t pitch;
+    uint8_t* y16;      // tiled kernel: when set, Y goes to the padded FP16 plane (Planes::y16) INSTEAD of the u8 plane
+    size_t pitch16;
     int plane_row0;
     const int* xofs;
     const short4* xcoef;
@@ -212,7 +218,7 @@ __device__ __forceinline__ unsigned long long f2_add_rn(unsigned long long a, un
 }
 
 template <int kTH>
-__global__ void __launch_bounds__(256) k_color_bicubic_tiled(ResizeDev p) {
+__global__ void __launch_bounds__(256, 5) k_color_bicubic_tiled(ResizeDev p) {   // 5 CTAs per SM: 48 registers (4 CTAs measured 6 % slower)
     __shared__ __align__(16) uint8_t sP[3][kMaxSR][kMaxSC + 8];   // +8: the 3-word window read of the last quad may run past a row
     // horizontal sums kept as float: they are integers below 2^24, so the conversion is exact and is done
     // once per sum instead of once per use in the vertical pass
@@ -332,8 +338,28 @@ __global__ void __launch_bounds__(256) k_color_bicubic_tiled(ResizeDev p) {
                         float v0, v1, v2, v3;
                         f2_unpack(va, v0, v1);
                         f2_unpack(vb, v2, v3);
+                        const uint32_t r0 = sat_u8_rn(v0), r1 = sat_u8_rn(v1), r2 = sat_u8_rn(v2), r3 = sat_u8_rn(v3);
+                        if (pl == 0 && p.y16) {   // Y as FP16 for the tcgen05 kernel's TMA staging; exact: 0x6400 | v is 1024 + v, minus 1024
+                            const __half2 k1024 = __float2half2_rn(1024.f);
+                            uint32_t a01 = (r0 | (r1 << 16)) | 0x64006400u, a23 = (r2 | (r3 << 16)) | 0x64006400u;
+                            __half2 h01 = __hsub2(*reinterpret_cast<__half2*>(&a01), k1024), h23 = __hsub2(*reinterpret_cast<__half2*>(&a23), k1024);
+                            const uint32_t w01 = *reinterpret_cast<uint32_t*>(&h01), w23 = *reinterpret_cast<uint32_t*>(&h23);
+                            uint8_t* o16 = p.y16 + (size_t)(dy - p.plane_row0) * p.pitch16 + 2 * (size_t)(dx + kY16Pad);
+                            *reinterpret_cast<uint2*>(o16) = make_uint2(w01, w23);
+                            if (dx == 0) {            // replicated columns -8..-1 (conv1 reads Y[clamp(c-4)], src/srcnn.cpp:279)
+                                const uint32_t e = __byte_perm(w01, 0, 0x1010);
+                                *reinterpret_cast<uint4*>(o16 - 2 * kY16Pad) = make_uint4(e, e, e, e);
+                            }
+                            if (dx + 4 >= p.ow) {     // this thread holds the last column: replicate it into W..W+7
+                                const unsigned short e = (unsigned short)(w23 >> 16);
+                                unsigned short* q16 = reinterpret_cast<unsigned short*>(o16) + 4;
+#pragma unroll
+                                for (int k = 0; k < 8; k++) q16[k] = e;
+                            }
+                            continue;
+                        }
                         uint8_t* outp = (pl == 0 ? p.y : (pl == 1 ? p.cr : p.cb)) + o;
-                        *reinterpret_cast<uint32_t*>(outp) = sat_u8_rn(v0) | (sat_u8_rn(v1) << 8) | (sat_u8_rn(v2) << 16) | (sat_u8_rn(v3) << 24);
+                        *reinterpret_cast<uint32_t*>(outp) = r0 | (r1 << 8) | (r2 << 16) | (r3 << 24);
                         continue;
                     }
                     const float4 h0 = *reinterpret_cast<const float4*>(&sH[pl][sr][col]);
@@ -343,15 +369,28 @@ __global__ void __launch_bounds__(256) k_color_bicubic_tiled(ResizeDev p) {
                     uint8_t* out = (pl == 0 ? p.y : (pl == 1 ? p.cr : p.cb)) + o;
                     {  // tile edge and/or cv::resize's integer scalar tail (last ow mod 8 columns)
                         const float hh[4][4] = {{h0.x, h0.y, h0.z, h0.w}, {h1.x, h1.y, h1.z, h1.w}, {h2.x, h2.y, h2.z, h2.w}, {h3.x, h3.y, h3.z, h3.w}};
-                        for (int j = 0; j < 4 && dx + j < dx1; j++)
-                            out[j] = (uint8_t)vertical_tap(__float2int_rn(hh[0][j]), __float2int_rn(hh[1][j]), __float2int_rn(hh[2][j]),
-                                                           __float2int_rn(hh[3][j]), cy, (dx + j) < p.simd_w);
+                        for (int j = 0; j < 4 && dx + j < dx1; j++) {
+                            const int r = vertical_tap(__float2int_rn(hh[0][j]), __float2int_rn(hh[1][j]), __float2int_rn(hh[2][j]),
+                                                       __float2int_rn(hh[3][j]), cy, (dx + j) < p.simd_w);
+                            if (pl == 0 && p.y16) {
+                                const unsigned short e = __half_as_ushort(__ushort2half_rn((unsigned short)r));
+                                unsigned short* q16 = reinterpret_cast<unsigned short*>(p.y16 + (size_t)(dy - p.plane_row0) * p.pitch16) + kY16Pad + dx + j;
+                                q16[0] = e;
+                                if (dx + j == 0)
+                                    for (int k = 1; k <= kY16Pad; k++) q16[-k] = e;
+                                if (dx + j == p.ow - 1)
+                                    for (int k = 1; k <= 8; k++) q16[k] = e;
+                            } else {
+                                out[j] = (uint8_t)r;
+                            }
+                        }
                     }
                 }
             }
         }
     }
 }
+
 
 int launch_color_bicubic(Ctx* c, const ResizeArgs& a) {
     ResizeDev p;
@@ -363,6 +402,7 @@ int launch_color_bicubic(Ctx* c, const ResizeArgs& a) {
     p.row_begin = a.row_begin; p.row_end = a.row_end;
     p.y = a.pl.y; p.cr = a.pl.cr; p.cb = a.pl.cb;
     p.pitch = a.pl.pitch;
+    p.y16 = nullptr; p.pitch16 = 0;
     p.plane_row0 = a.pl.row0;
     p.xofs = a.tx->d_ofs; p.xcoef = a.tx->d_coef;
     p.yofs = a.ty->d_ofs; p.ycoef = a.ty->d_coef;
@@ -389,6 +429,7 @@ int launch_color_bicubic(Ctx* c, const ResizeArgs& a) {
     p.quad_ok = 1;
     for (int dx = 0; dx + 3 < a.ow && p.quad_ok; dx += 4)
         if (a.tx->h_ofs[dx + 3] - a.tx->h_ofs[dx] > 4) p.quad_ok = 0;
+    p.y16 = a.pl.y16; p.pitch16 = a.pl.pitch16;       // tiled kernel: the tcgen05 path's Y goes straight to the padded FP16 plane
     if (th) {
         dim3 grid((a.ow + kTW - 1) / kTW, (rows + th - 1) / th);
         if (th == 64) k_color_bicubic_tiled<64><<<grid, 256, 0, c->stream>>>(p);
@@ -397,6 +438,39 @@ int launch_color_bicubic(Ctx* c, const ResizeArgs& a) {
         dim3 grid((a.ow + 31) / 32, (rows + 7) / 8);
         k_color_bicubic_direct<<<grid, 256, 0, c->stream>>>(p);
     }
+    c->launches++;
+    SRCNN_CUDA(c, cudaGetLastError());
+    if (!th && a.pl.y16)   // the direct kernel (strong down-scales) writes the u8 plane: the FP16 copy is a pass of its own there
+        return launch_y8_to_y16(c, a.pl.y, a.pl.pitch, a.ow, rows, a.pl.y16, a.pl.pitch16);
+    return SRCNN_OK;
+}
+
+// u8 Y plane -> padded FP16 plane (Planes::y16): 8 pixels per thread; the first / last group of a row also writes the
+// replicated edge columns.  Off the hot path (the tiled kernel writes FP16 itself): stage API and fallback geometries.
+__global__ void __launch_bounds__(256) k_y8_to_y16(const uint8_t* __restrict__ y, size_t pitch, int w, int rows, uint8_t* __restrict__ y16,
+                                                   size_t pitch16, int groups) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int row = (int)(gid / groups), g = (int)(gid - (long long)row * groups);
+    if (row >= rows) return;
+    const uint8_t* src = y + (size_t)row * pitch;
+    unsigned short* dst = reinterpret_cast<unsigned short*>(y16 + (size_t)row * pitch16) + kY16Pad;
+    const int x0 = g * 8;
+    for (int j = 0; j < 8 && x0 + j < w; j++) dst[x0 + j] = __half_as_ushort(__ushort2half_rn((unsigned short)src[x0 + j]));
+    if (g == 0) {
+        const unsigned short e = __half_as_ushort(__ushort2half_rn((unsigned short)src[0]));
+        for (int k = 1; k <= kY16Pad; k++) dst[-k] = e;
+    }
+    if (x0 <= w - 1 && w - 1 < x0 + 8) {
+        const unsigned short e = __half_as_ushort(__ushort2half_rn((unsigned short)src[w - 1]));
+        for (int k = 0; k < 8; k++) dst[w + k] = e;
+    }
+}
+
+int launch_y8_to_y16(Ctx* c, const uint8_t* y, size_t pitch, int w, int rows, uint8_t* y16, size_t pitch16) {
+    if (rows <= 0 || w <= 0) return SRCNN_OK;
+    const int groups = (w + 7) / 8;
+    const long long total = (long long)groups * rows;
+    k_y8_to_y16<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(y, pitch, w, rows, y16, pitch16, groups);
     c->launches++;
     SRCNN_CUDA(c, cudaGetLastError());
     return SRCNN_OK;
@@ -449,7 +523,28 @@ __global__ void __launch_bounds__(256) k_merge_ycc2bgr(const uint8_t* __restrict
     }
 }
 
-// 16 pixels per thread: three 128-bit plane loads, three 128-bit stores (needs 16-byte aligned rows)
+// 16 pixels per thread: three 128-bit plane loads, three 128-bit stores (needs 16-byte aligned rows).  Arithmetic per pixel
+// (bit-identical to ycc_to_bgr above): with t = Y * 2^14 + 8192, every channel is (t + chroma term) >> 14 -- adding a
+// multiple of 2^14 before the shift is adding Y after it -- and each chroma term is ONE dp2a: (Cb-128, Cr-128) as a pair of
+// signed bytes (x ^ 0x80) times a pair of 16-bit coefficients.  Saturation and byte packing are cvt.pack.sat.u8.s32 (two
+// channels per instruction).  ~10 instructions per pixel instead of ~25; R/B order is a choice of coefficient pairs.
+__device__ __forceinline__ int dp2a_lo_ss(uint32_t a, uint32_t b, int c) {
+    int d;
+    asm("dp2a.lo.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp2a_hi_ss(uint32_t a, uint32_t b, int c) {
+    int d;
+    asm("dp2a.hi.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+// d = sat_u8(lo) | sat_u8(hi) << 8 | (upper & 0xFFFF) << 16
+__device__ __forceinline__ uint32_t pack_sat_u8(int lo, int hi, uint32_t upper) {
+    uint32_t d;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(hi), "r"(lo), "r"(upper));
+    return d;
+}
+
 __global__ void __launch_bounds__(256) k_merge_ycc2bgr_v16(const uint8_t* __restrict__ y, const uint8_t* __restrict__ cr,
                                                            const uint8_t* __restrict__ cb, size_t pitch, int w, int rows,
                                                            int swapRB, uint8_t* __restrict__ dst, size_t dst_stride,
@@ -463,21 +558,33 @@ __global__ void __launch_bounds__(256) k_merge_ycc2bgr_v16(const uint8_t* __rest
     const uint4 vr = *reinterpret_cast<const uint4*>(cr + o);
     const uint4 vb = *reinterpret_cast<const uint4*>(cb + o);
     const uint32_t wy[4] = {vy.x, vy.y, vy.z, vy.w}, wr[4] = {vr.x, vr.y, vr.z, vr.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
+    // 16-bit coefficient pairs (low half x Cb-128, high half x Cr-128): B = 29049 cb, G = -5636 cb - 11698 cr, R = 22987 cr
+    const uint32_t kB = 29049u, kG = (uint32_t)(unsigned short)(-5636) | ((uint32_t)(unsigned short)(-11698) << 16), kR = 22987u << 16;
+    const uint32_t k0 = swapRB ? kR : kB, k2 = swapRB ? kB : kR;      // first and third byte of a pixel
     uint32_t outw[12];
 #pragma unroll
     for (int k = 0; k < 4; k++) {   // 4 pixels -> 12 bytes -> 3 words
-        uint32_t px[12];
+        const uint32_t sb = wb[k] ^ 0x80808080u, sr = wr[k] ^ 0x80808080u;     // Cb-128, Cr-128 as signed bytes
+        const uint32_t c01 = __byte_perm(sb, sr, 0x5140), c23 = __byte_perm(sb, sr, 0x7362);   // (cb0,cr0,cb1,cr1), (cb2,cr2,cb3,cr3)
+        int v[4][3];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            int B, G, R;
-            ycc_to_bgr((wy[k] >> (8 * j)) & 255, (wr[k] >> (8 * j)) & 255, (wb[k] >> (8 * j)) & 255, B, G, R);
-            px[3 * j] = (uint32_t)(swapRB ? R : B);
-            px[3 * j + 1] = (uint32_t)G;
-            px[3 * j + 2] = (uint32_t)(swapRB ? B : R);
+            const int t = (int)((wy[k] >> (8 * j)) & 255u) * 16384 + 8192;
+            const uint32_t cc = j < 2 ? c01 : c23;
+            if (j & 1) {
+                v[j][0] = dp2a_hi_ss(k0, cc, t) >> 14;
+                v[j][1] = dp2a_hi_ss(kG, cc, t) >> 14;
+                v[j][2] = dp2a_hi_ss(k2, cc, t) >> 14;
+            } else {
+                v[j][0] = dp2a_lo_ss(k0, cc, t) >> 14;
+                v[j][1] = dp2a_lo_ss(kG, cc, t) >> 14;
+                v[j][2] = dp2a_lo_ss(k2, cc, t) >> 14;
+            }
         }
-        outw[3 * k] = px[0] | (px[1] << 8) | (px[2] << 16) | (px[3] << 24);
-        outw[3 * k + 1] = px[4] | (px[5] << 8) | (px[6] << 16) | (px[7] << 24);
-        outw[3 * k + 2] = px[8] | (px[9] << 8) | (px[10] << 16) | (px[11] << 24);
+        // bytes: p0c0 p0c1 p0c2 p1c0 | p1c1 p1c2 p2c0 p2c1 | p2c2 p3c0 p3c1 p3c2
+        outw[3 * k] = pack_sat_u8(v[0][0], v[0][1], pack_sat_u8(v[0][2], v[1][0], 0u));
+        outw[3 * k + 1] = pack_sat_u8(v[1][1], v[1][2], pack_sat_u8(v[2][0], v[2][1], 0u));
+        outw[3 * k + 2] = pack_sat_u8(v[2][2], v[3][0], pack_sat_u8(v[3][1], v[3][2], 0u));
     }
     uint8_t* d = dst + (size_t)row * dst_stride + 3 * (size_t)x;
     if (x + 15 < w) {

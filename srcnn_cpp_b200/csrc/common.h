@@ -60,6 +60,10 @@ struct TapTable {
 // Planes are u8, `pitch` bytes per row (multiple of 128), `rows` rows starting at output row `row0`.
 struct Planes {
     uint8_t* y = nullptr;
+    // FP16 copy of the Y plane for the tcgen05 kernel's TMA staging: element (row, x) at index x + kY16Pad of its row, columns
+    // -kY16Pad..-1 and W..W+7 hold the replicated edge pixels, rows are `pitch16` BYTES apart (a multiple of 16)
+    uint8_t* y16 = nullptr;
+    size_t pitch16 = 0;
     uint8_t* cr = nullptr;
     uint8_t* cb = nullptr;
     uint8_t* yout = nullptr;
@@ -68,9 +72,33 @@ struct Planes {
 };
 
 // row-walking kernel: the cached cut of a launch's row steps over its pipelines (srcnn_tc2.cu, tc2_partition)
+constexpr int kY16Pad = 8;
+inline size_t y16_pitch_bytes(int w) { return ((size_t)w + 144 + 7) / 8 * 8 * 2; }   // the last strip's 144-column copy stays inside the row
+
 struct Tc2Partition {
     int nstrips = 0, hb = 0, nworkers = 0, ovh = -1;
     std::vector<long long> bounds;
+};
+
+// host-buffer pipeline as a CUDA graph: everything a replay depends on
+struct PipeKey {
+    const void* src;
+    void* dst;
+    int n, w, h;
+    size_t src_stride, src_frame_stride;
+    int order;
+    float scale;
+    int R0, R1;
+    size_t dst_stride, dst_frame_stride;
+    int variant, fuse, host_bands, ka_kernel, ka_rows, seg_ovh;
+    void* stream;
+};
+struct PipeGraph {
+    PipeKey key;
+    cudaGraphExec_t exec = nullptr;
+    bool failed = false;
+    long long kernel_launches = 0;      // kernels one replay launches (for srcnn_launch_count)
+    unsigned long long stamp = 0;
 };
 
 struct Ctx {
@@ -95,7 +123,8 @@ struct Ctx {
     int* d_guard = nullptr;          // device-side watchdog flag (mapped pinned)
     int* h_guard = nullptr;
 
-    DevBuf plane_buf;   // Y, Cr, Cb, Y' planes
+    DevBuf plane_buf;   // Y, Cr, Cb, Y' planes (+ the FP16 Y plane)
+    DevBuf y16_buf;     // stage API: FP16 copy of a caller's u8 Y plane
     DevBuf act2_buf;    // FP32 variant: conv2 activations (32 float planes) of one row chunk
     DevBuf src_buf;     // device copy of a host source image / batch
     DevBuf dst_buf;     // device copy of the result before D2H
@@ -109,6 +138,12 @@ struct Ctx {
     cudaStream_t s_in = nullptr, s_out = nullptr;
     std::vector<cudaEvent_t> pipe_events;
 
+    // CUDA-graph replay of repeated host-buffer calls (api.cu, host_pipeline)
+    std::vector<PipeGraph> graphs;
+    unsigned long long graph_clock = 0;
+    bool use_graphs = true;          // SRCNN_GRAPHS=0 switches it off
+    bool capturing = false;
+
     // optional per-stage device timing (srcnn_profile_*): 4 events per band processed, prof_calls counts the API calls
     bool profiling = false;
     std::vector<cudaEvent_t> ev_pool;
@@ -119,6 +154,7 @@ struct Ctx {
 int prof_mark(Ctx* c);   // records the next event of the pool on c->stream when profiling is on
 
 int ensure(Ctx* c, DevBuf& b, size_t bytes);
+void drop_graphs(Ctx* c);
 int get_taps(Ctx* c, int src, int dst, TapTable** out);
 void build_cubic_taps(int src, int dst, int* ofs, short4* coef);
 
@@ -150,6 +186,8 @@ struct MergeArgs {
     size_t dst_stride;
 };
 int launch_merge(Ctx* c, const MergeArgs& a);
+// u8 Y plane -> FP16 plane in the Planes::y16 layout (replicated edge columns included)
+int launch_y8_to_y16(Ctx* c, const uint8_t* y, size_t pitch, int w, int rows, uint8_t* y16, size_t pitch16);
 
 // CNN on a plane band.  y points at plane row 0 which is image row `row0`; the plane holds image rows
 // [row0, row0+rows).  Produces image rows [out_begin, out_end) into `out` (same row0 convention).
@@ -157,6 +195,8 @@ int launch_merge(Ctx* c, const MergeArgs& a);
 struct CnnArgs {
     const uint8_t* y;
     size_t pitch;
+    const uint8_t* y16 = nullptr;   // FP16 Y plane (Planes::y16 layout), same row0 convention; tcgen05 variant: built from y when null
+    size_t pitch16 = 0;
     int W, H;
     int row0, rows;
     int out_begin, out_end;

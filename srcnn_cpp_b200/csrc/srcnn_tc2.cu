@@ -65,7 +65,7 @@ constexpr int kB1Bytes = kSlots * kB1Var;         // 143 360
 constexpr int kB2Bytes = 5 * 32 * 16 * 2;         // 4 K steps + bias step
 constexpr int kB3Bytes = 2 * 32 * 16 * 2;
 constexpr int kWeightBytes = kB1Bytes + kB2Bytes + kB3Bytes;   // 150 528
-constexpr int kYRowBytes = 288;                   // staged Y row: 2 pad + 136 px + 6 pad FP16
+constexpr int kYRowBytes = 288;                   // staged Y row: 144 FP16 = one TMA bulk copy (the 136 tile columns start 2 or 6 in)
 constexpr int kYSlots = 4;
 constexpr int kHxBytes = 2 * 5 * 128 * 4;         // horizontal-tap exchange, double buffered: [buf][n][lane] fp32
 
@@ -75,7 +75,7 @@ constexpr int kImgB3 = kImgB2 + kB2Bytes;
 constexpr int kOffY = kOffW + kWeightBytes;
 constexpr int kOffHx = kOffY + 2 * kYSlots * kYRowBytes;
 constexpr int kOffBar = kOffHx + 2 * kHxBytes;
-constexpr int kBarsPerPipe = 9;                   // D1full[3] D2full[3] Tfull[3]: completion barriers of tcgen05.commit
+constexpr int kBarsPerPipe = 13;                  // D1full[3] D2full[3] Tfull[3]: completion barriers of tcgen05.commit; Yfull[4]: staged rows (TMA)
 constexpr int kCtrBytes = 32;                     // per pipeline: freed[4] (T rows consumed, one per E3 warp), c1done, pad
 constexpr int kOffCtr = (kOffBar + 8 + 2 * kBarsPerPipe * 8 + 15) / 16 * 16;   // 16-byte aligned: freed[4] is read with one 128-bit load
 constexpr int kOffTmem = kOffCtr + 2 * kCtrBytes;
@@ -302,8 +302,9 @@ __device__ __forceinline__ uint32_t relu_pack_f16x2(float lo, float hi) {
 // kernel parameters
 // ---------------------------------------------------------------------------------------------
 struct Params {
-    const uint8_t* y;      // plane row 0 = image row `row0`; rows [row0, row0+rows) are present
-    size_t pitch;
+    const uint8_t* y16;    // FP16 Y plane (kY16Pad replicated columns left, >= 6 right), row 0 = image row `row0`; rows [row0, row0+rows)
+    size_t pitch16;        // its row pitch in BYTES (multiple of 16)
+    size_t pitch;          // row pitch of the u8 chroma planes (fused merge only)
     int W, H;
     int row0, rows;
     int out_begin, out_end;  // image rows to produce
@@ -353,7 +354,6 @@ __device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_shared_u16(uint32_t addr, unsigned short v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory"); }
 // same for the sixteen ring-row barriers
 struct RingCursor {
     uint32_t idx = 0, par = 0;
@@ -498,7 +498,8 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
     UnitCursor uc;                   // this role's row cursor over the pipeline's three units
     uint32_t rows_done = 0;          // conv1 issuer: rows issued so far (the first three find their unit free)
     uint32_t npub = 0;               // E3: rows published to the horizontal exchange so far
-    (void)rows_done; (void)npub;
+    uint32_t ycount = 0;             // producer: Y rows staged so far (slot and mbarrier phase of the TMA staging ring)
+    (void)rows_done; (void)npub; (void)ycount;
 
     if constexpr (ROLE == 1) {   // the ring starts as finite zeros (stale TMEM bits could be NaN: 0 x NaN = NaN) + the ones column
         uint32_t z[32];
@@ -616,35 +617,28 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
             // ================= im2col ring producer =================
             const int ybar = 1 + pipe;
             const uint32_t yst_s = sbase + kOffY + pipe * (kYSlots * kYRowBytes);
-            // Staging the next Y row (global load, u8 -> FP16, shared store) is left to the three warps that do NOT issue conv1:
-            // the issuing warp's serial chain is the pipeline's bottleneck.  96 lanes cover the 136 tile columns: s and
-            // 96 + s mod 40 (lanes 40.. repeat a column: same value, no divergence).
-            const int myq = tp >> 5, issq = pipe;                            // this warp's quarter, the issuing quarter
-            const int sidx = (myq - (myq > issq ? 1 : 0)) * 32 + (tp & 31);  // 0..95 over the staging lanes
-            const int sj1 = 96 + sidx % 40;
-            const int xc0 = min(max(xs - 6 + sidx, 0), W - 1);               // tile column sidx
-            const int xc1 = min(max(xs - 6 + sj1, 0), W - 1);                // tile column 96 + sidx mod 40
-            // Y of ring rows 0, 1, 2, ... at this thread's tile columns.  The plane row of ring row q is
-            // clamp(clamp(ta-4+q, 0, H-1) - row0, 0, rows-1): it advances by 0 or 1 per ring row, so the two row pointers are
-            // carried and bumped by the pitch (no 64-bit multiply in the row loop; a 65536^2 image overflows 32-bit offsets)
+            const uint32_t ymb = bars + 9 * 8;                      // Yfull[4]: one mbarrier per staging slot
+            // Y rows arrive by TMA: one cp.async.bulk of 288 bytes per ring row, straight from the FP16 plane the colour+bicubic
+            // kernel wrote (replicate-padded columns, so the copy never needs a border case), issued two rows ahead by one lane of
+            // a warp that does NOT issue conv1 (the issuing warp's serial chain is the pipeline's bottleneck); the same warp waits
+            // for the row's bytes in front of the row barrier, so nobody else ever polls.  A strip starts at plane index
+            // xs + 2 = 124 s + 2: the copy starts 2 (even strips) or 6 (odd strips) halves earlier, where the address is a
+            // multiple of 16 bytes.
+            const bool copier = (tp >> 5) == ((pipe + 1) & 3);
+            const int odd = strip & 1;
+            const uint32_t tile_off = 4u + 8u * (uint32_t)odd;      // byte offset of tile column 0 (image column xs - 6) in a staged row
+            // The plane row of ring row q is clamp(clamp(ta-4+q, 0, H-1) - row0, 0, rows-1)
             auto plane_row = [&](int q) { return min(max(min(max(ta - 4 + q, 0), H - 1) - p.row0, 0), p.rows - 1); };
-            int prow = plane_row(0);
-            const uint8_t* yp0 = p.y + (size_t)prow * p.pitch + xc0;
-            const uint8_t* yp1 = p.y + (size_t)prow * p.pitch + xc1;
-            const size_t ypitch = p.pitch;
-            auto fetch = [&](int q, uint32_t& v0, uint32_t& v1) {   // must be called with q = 0, 1, 2, ... in order
-                if (warp0) return;
-                const int r = plane_row(q);
-                if (r != prow) { yp0 += ypitch; yp1 += ypitch; prow = r; }
-                v0 = *yp0;
-                v1 = *yp1;   // no arithmetic on the loaded values here: nothing waits for the loads
+            const uint8_t* ysrc = p.y16 + 2 * (size_t)(xs - 4 * odd);
+            const uint32_t ybase = ycount;                          // staged rows before this segment: slot and phase run on
+            auto issue_row = [&](int q) {                           // one lane
+                const uint32_t k = ybase + (uint32_t)q, sl = k & (kYSlots - 1);
+                mbar_expect_tx(ymb + sl * 8, kYRowBytes);
+                bulk_g2s(yst_s + sl * kYRowBytes, ysrc + (size_t)plane_row(q) * p.pitch16, kYRowBytes, ymb + sl * 8);
             };
-            const uint32_t st_my = yst_s + 4 + sidx * 2, st_x = yst_s + 4 + sj1 * 2;
-            auto stage = [&](int q, uint32_t v0, uint32_t v1) {   // exact u8 -> FP16 (integers below 2048 are exact)
-                if (warp0) return;
-                const uint32_t ro = (q & (kYSlots - 1)) * kYRowBytes;
-                st_shared_u16(st_my + ro, __half_as_ushort(__ushort2half_rn((unsigned short)v0)));
-                st_shared_u16(st_x + ro, __half_as_ushort(__ushort2half_rn((unsigned short)v1)));
+            auto wait_row = [&](int q) {                            // the copier warp
+                const uint32_t k = ybase + (uint32_t)q;
+                mbar_wait(ymb + (k & (kYSlots - 1)) * 8, (k >> 2) & 1u, wd, p.guard, 31);
             };
             uint32_t slot = slot0;
             uint32_t seen_f[4] = {0u, 0u, 0u, 0u}, seen_c = 0u;   // progress counters as seen one row ago
@@ -653,10 +647,10 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
             // One ring row per step.  A single named barrier per row says three things at once: every lane has written ring
             // row t (conv1 of row t-8 may be issued), row t+1 is staged in shared memory, and (warp 0 checked it) the slot of
             // row t+1 is no longer read by any conv1.
-            auto step = [&](int t, uint32_t& nxt0, uint32_t& nxt1) {
+            auto step = [&](int t) {
                 TL2(1, t, 0);
-                // 9 taps of lane tp = tile columns tp .. tp+8 = FP16 index 2 + tp .. of the staged row
-                const uint32_t rowaddr = yst_s + (t & (kYSlots - 1)) * kYRowBytes + 4 + ((tp >> 1) << 2);
+                // 9 taps of lane tp = tile columns tp .. tp+8 of the staged row
+                const uint32_t rowaddr = yst_s + ((ybase + (uint32_t)t) & (kYSlots - 1)) * kYRowBytes + tile_off + ((tp >> 1) << 2);
                 uint32_t w[6], o[5];
 #pragma unroll
                 for (int k = 0; k < 6; k++) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w[k]) : "r"(rowaddr + 4 * k));
@@ -668,9 +662,10 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
                 const uint32_t sl = tml + kRingOff + slot * kSlotCols;
                 tmem_st4(sl, o[0], o[1], o[2], o[3]);
                 tmem_st1(sl + 4, o[4]);
-                if (t + 1 < nP) stage(t + 1, nxt0, nxt1);   // loaded one full step ago
-                if (t + 2 < nP) fetch(t + 2, nxt0, nxt1);   // issued AFTER the use above: the scoreboard the conversion waits on
-                                                            // must not also count a load that has just been issued
+                if (copier) {   // row t+2 goes out (its slot held row t-2, read two row barriers ago); row t+1 must have landed
+                    if (leader && t + 2 < nP) issue_row(t + 2);
+                    if (t + 1 < nP) wait_row(t + 1);
+                }
                 TL2(1, t, 2);
                 tc_wait_st();
                 tc_fence_before();
@@ -716,12 +711,16 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
                 }
                 if (++slot == (uint32_t)kSlots) slot = 0;
             };
-            uint32_t a0 = 0, a1 = 0;
-            fetch(0, a0, a1);
-            stage(0, a0, a1);
-            if (nP > 1) fetch(1, a0, a1);
+            if (copier) {
+                if (leader) {
+                    issue_row(0);
+                    if (nP > 1) issue_row(1);
+                }
+                wait_row(0);
+            }
             named_bar(ybar, 128);   // row 0 staged
-            for (int t = 0; t < nP; t++) step(t, a0, a1);
+            for (int t = 0; t < nP; t++) step(t);
+            ycount += (uint32_t)nP;
         } else {
             // ================= E3: conv3 tap sums =================
             const uint32_t hx_s = sbase + kOffHx + pipe * kHxBytes;
@@ -951,11 +950,20 @@ void tc2_partition(int nstrips, int hb, int nworkers, int ovh, long long* bounds
     // would show as bounds[nworkers] < total, which the walk above rules out
 }
 
-int launch_cnn_tc2(Ctx* c, const CnnArgs& a) {
+int launch_cnn_tc2(Ctx* c, const CnnArgs& a0) {
     using namespace tc2;
-    if (a.out_end <= a.out_begin) return SRCNN_OK;
+    if (a0.out_end <= a0.out_begin) return SRCNN_OK;
+    CnnArgs a = a0;
+    if (!a.y16) {   // a caller's u8 plane (stage API): the kernel's TMA staging wants the padded FP16 form
+        a.pitch16 = y16_pitch_bytes(a.W);
+        int rc = ensure(c, c->y16_buf, a.pitch16 * (size_t)a.rows + 512);
+        if (rc) return rc;
+        rc = launch_y8_to_y16(c, a.y, a.pitch, a.W, a.rows, (uint8_t*)c->y16_buf.p, a.pitch16);
+        if (rc) return rc;
+        a.y16 = (const uint8_t*)c->y16_buf.p;
+    }
     Params p;
-    p.y = a.y; p.pitch = a.pitch;
+    p.y16 = (const uint8_t*)a.y16; p.pitch16 = a.pitch16; p.pitch = a.pitch;
     p.W = a.W; p.H = a.H;
     p.row0 = a.row0; p.rows = a.rows;
     p.out_begin = a.out_begin; p.out_end = a.out_end;

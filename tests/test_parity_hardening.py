@@ -112,7 +112,7 @@ def test_bgr_bound_is_inherited_from_y(engine, oracle):
     d = torch.from_numpy(img).to("cuda:0")
     y, cr, cb = [torch.zeros((400, 640), dtype=torch.uint8, device="cuda:0")[:, :600] for _ in range(3)]
     engine.stage_color_bicubic(d, 2.0, y, cr, cb)
-    yo = torch.zeros_like(y)
+    yo = torch.zeros((400, 640), dtype=torch.uint8, device="cuda:0")[:, :600]   # same pitch as the other planes
     engine.stage_cnn(y, yo, variant=S.VARIANT_TC)
     out = torch.zeros((400, 600, 3), dtype=torch.uint8, device="cuda:0")
     engine.stage_merge(yo, cr, cb, out)
