@@ -434,6 +434,29 @@ def run_ours(args, cfg, rank, world, local_rank):
         e2e_ms_wall = (time.perf_counter() - t0) * 1e3
         e2e_ms_step = max(f0.elapsed_time(f1), e2e_ms_wall) / e2e_steps   # the call blocks until dst is ready: wall >= device
         barrier()
+    # ---- the copies alone: the same bytes per step over PCIe, H2D and D2H concurrently on two streams, all ranks at once.
+    # No kernel can make the host-buffer call faster than this (the e2e ceiling of THIS box with THIS many GPUs busy).
+    copy_ms_step = float("nan")
+    if e2e_step is not None and wk["h2d"] > 0:
+        hin, hout = torch.empty(wk["h2d"], dtype=torch.uint8).pin_memory(), torch.empty(wk["d2h"], dtype=torch.uint8).pin_memory()
+        din, dout = torch.empty(wk["h2d"], dtype=torch.uint8, device=dev), torch.empty(wk["d2h"], dtype=torch.uint8, device=dev)
+        s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        reps = 10 if wk["d2h"] < (1 << 28) else 3
+
+        def copies(k):
+            for _ in range(k):
+                with torch.cuda.stream(s1):
+                    din.copy_(hin, non_blocking=True)
+                with torch.cuda.stream(s2):
+                    hout.copy_(dout, non_blocking=True)
+        copies(2)
+        barrier()
+        t0 = time.perf_counter()
+        copies(reps)
+        torch.cuda.synchronize()
+        copy_ms_step = (time.perf_counter() - t0) * 1e3 / reps
+        barrier()
+        del hin, hout, din, dout
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -441,10 +464,10 @@ def run_ours(args, cfg, rank, world, local_rank):
     assert wk["check"]() > 0
 
     # max over ranks
-    t = torch.tensor([ms_total, e2e_ms_step, stage_ms[0], stage_ms[1], stage_ms[2]], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, e2e_ms_step, stage_ms[0], stage_ms[1], stage_ms[2], copy_ms_step], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms_step, a_ms, b_ms, c_ms = [float(x) for x in t.tolist()]
+    ms_total, e2e_ms_step, a_ms, b_ms, c_ms, copy_ms_step = [float(x) for x in t.tolist()]
 
     if rank == 0:
         peaks = load_peaks()
@@ -491,6 +514,11 @@ def run_ours(args, cfg, rank, world, local_rank):
         }
         if wk["e2e_note"]:
             line["e2e"]["note"] = wk["e2e_note"]
+        if copy_ms_step == copy_ms_step:   # not NaN
+            line["e2e"].update({"copy_only_ms_per_step": copy_ms_step,
+                                "pcie_ceiling_GBs": world * (wk["h2d"] + wk["d2h"]) / (copy_ms_step * 1e-3) / 1e9,
+                                "frac_of_copy_ceiling": copy_ms_step / e2e_ms_step,
+                                "ceiling": "the step's H2D and D2H bytes alone, pinned, concurrently on two streams, all ranks at once (max over ranks)"})
         if world == 1 and not args.no_cpu:
             run, kind, threads, desc = cpu_reference_runner(s)
             v, sample, _ = time_cpu(run, cfg, args.cpu_budget)

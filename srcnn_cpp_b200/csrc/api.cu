@@ -75,19 +75,23 @@ static int check_image(Ctx* c, const void* src, int w, int h, size_t stride, int
     return SRCNN_OK;
 }
 
-static int carve_planes(Ctx* c, int ow, int rows, int row0, Planes* pl) {
+// planes of `nframes` same-sized frames: [Y frames][Cr frames][Cb frames][Y' frames][FP16 Y frames]
+static int carve_planes(Ctx* c, int ow, int rows, int row0, Planes* pl, int nframes = 1) {
     const size_t pitch = align_up((size_t)ow, 128);
     const size_t plane = pitch * (size_t)rows;
     const size_t pitch16 = y16_pitch_bytes(ow);
-    const size_t plane16 = align_up(pitch16 * (size_t)rows + 512, 256);   // slack: the last row's last strip copy may run past the row
-    int rc = ensure(c, c->plane_buf, plane * 4 + plane16);
+    const size_t plane16 = align_up(pitch16 * (size_t)rows, 256);
+    const size_t nf = (size_t)nframes;
+    int rc = ensure(c, c->plane_buf, (plane * 4 + plane16) * nf + 512);   // slack: the last row's last strip copy may run past the row
     if (rc) return rc;
     uint8_t* base = (uint8_t*)c->plane_buf.p;
     pl->y = base;
-    pl->cr = base + plane;
-    pl->cb = base + 2 * plane;
-    pl->yout = base + 3 * plane;
-    pl->y16 = base + 4 * plane;
+    pl->cr = base + plane * nf;
+    pl->cb = base + 2 * plane * nf;
+    pl->yout = base + 3 * plane * nf;
+    pl->y16 = base + 4 * plane * nf;
+    pl->frame_stride = plane;
+    pl->frame_stride16 = plane16;
     pl->pitch16 = pitch16;
     pl->pitch = pitch;
     pl->row0 = row0;
@@ -172,6 +176,85 @@ static int process_rows(Ctx* c, const uint8_t* d_src, int w, int h, size_t src_s
     const size_t ev0 = c->ev_used;
     const int rc = process_rows_impl(c, d_src, w, h, src_stride, s0, s1, order, scale, ow, oh, r0, r1, d_dst, dst_stride);
     if (rc) c->ev_used = ev0;        // a failed band leaves no half-recorded event group behind (srcnn_profile_read pairs by 4)
+    else c->fail_stage = SRCNN_STAGE_NONE;
+    return rc;
+}
+
+// `n` whole frames resident on the device, in chunks whose planes stay below ~1 GB: per chunk ONE launch of each stage -- the
+// colour+bicubic grid gets a frame dimension, the row-walking kernel sees the frames as more strips of one work list (no
+// per-frame pipeline fill / drain), the merge kernel sees the chunk's planes as one tall image.
+static int process_frames_impl(Ctx* c, const uint8_t* d_src, int n, int w, int h, size_t src_stride, size_t src_frame_stride, int order,
+                               float scale, int ow, int oh, uint8_t* d_dst, size_t dst_stride, size_t dst_frame_stride) {
+    TapTable *tx, *ty;
+    c->fail_stage = SRCNN_STAGE_COLOR_BICUBIC;
+    int rc = get_taps(c, w, ow, &tx);
+    if (rc) return rc;
+    if ((rc = get_taps(c, h, oh, &ty))) return rc;
+    const size_t per_frame = align_up((size_t)ow, 128) * (size_t)oh * 4 + y16_pitch_bytes(ow) * (size_t)oh;
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n, ((size_t)1 << 30) / per_frame));
+    for (int f0 = 0; f0 < n; f0 += chunk) {
+        const int m = std::min(chunk, n - f0);
+        Planes pl;
+        c->fail_stage = SRCNN_STAGE_PLANES;
+        if ((rc = carve_planes(c, ow, oh, 0, &pl, m))) return rc;
+        c->fail_stage = SRCNN_STAGE_COLOR_BICUBIC;
+        ResizeArgs ra;
+        ra.src = d_src + (size_t)f0 * src_frame_stride; ra.src_stride = src_stride;
+        ra.sw = w; ra.sh = h; ra.src_row0 = 0; ra.src_row1 = h;
+        ra.order = order;
+        ra.ow = ow; ra.oh = oh;
+        ra.row_begin = 0; ra.row_end = oh;
+        ra.pl = pl; ra.tx = tx; ra.ty = ty;
+        ra.nframes = m; ra.src_frame_stride = src_frame_stride;
+        if ((rc = prof_mark(c))) return rc;
+        if ((rc = launch_color_bicubic(c, ra))) return rc;
+        if ((rc = prof_mark(c))) return rc;
+        c->fail_stage = SRCNN_STAGE_CNN;
+        CnnArgs ca;
+        ca.y = pl.y; ca.pitch = pl.pitch;
+        ca.y16 = pl.y16; ca.pitch16 = pl.pitch16;
+        ca.W = ow; ca.H = oh;
+        ca.row0 = 0; ca.rows = oh;
+        ca.out_begin = 0; ca.out_end = oh;
+        ca.out = pl.yout; ca.out_pitch = pl.pitch;
+        ca.nframes = m; ca.y16_frame_stride = pl.frame_stride16; ca.out_frame_stride = pl.frame_stride;
+        if ((rc = launch_cnn_tc2(c, ca))) return rc;
+        if ((rc = prof_mark(c))) return rc;
+        c->fail_stage = SRCNN_STAGE_MERGE;
+        MergeArgs ma;
+        ma.y = pl.yout; ma.cr = pl.cr; ma.cb = pl.cb;
+        ma.pitch = pl.pitch; ma.w = ow;
+        ma.order = order;
+        uint8_t* dst0 = d_dst + (size_t)f0 * dst_frame_stride;
+        if (m == 1 || dst_frame_stride == dst_stride * (size_t)oh) {   // the chunk's results are one tall image too
+            ma.rows = oh * m; ma.dst = dst0; ma.dst_stride = dst_stride;
+            if ((rc = launch_merge(c, ma))) return rc;
+        } else {
+            for (int f = 0; f < m; f++) {
+                ma.y = pl.yout + (size_t)f * pl.frame_stride; ma.cr = pl.cr + (size_t)f * pl.frame_stride; ma.cb = pl.cb + (size_t)f * pl.frame_stride;
+                ma.rows = oh; ma.dst = dst0 + (size_t)f * dst_frame_stride; ma.dst_stride = dst_stride;
+                if ((rc = launch_merge(c, ma))) return rc;
+            }
+        }
+        if ((rc = prof_mark(c))) return rc;
+    }
+    return SRCNN_OK;
+}
+
+static int process_frames(Ctx* c, const uint8_t* d_src, int n, int w, int h, size_t src_stride, size_t src_frame_stride, int order,
+                          float scale, int ow, int oh, uint8_t* d_dst, size_t dst_stride, size_t dst_frame_stride) {
+    // one launch per stage and chunk needs the row-walking kernel with a separate merge; everything else goes frame by frame
+    if (n == 1 || c->variant != SRCNN_VARIANT_TC || c->fuse_merge || !c->batch_launch) {
+        for (int f = 0; f < n; f++) {
+            int rc = process_rows(c, d_src + (size_t)f * src_frame_stride, w, h, src_stride, 0, h, order, scale, ow, oh, 0, oh,
+                                  d_dst + (size_t)f * dst_frame_stride, dst_stride);
+            if (rc) return rc;
+        }
+        return SRCNN_OK;
+    }
+    const size_t ev0 = c->ev_used;
+    const int rc = process_frames_impl(c, d_src, n, w, h, src_stride, src_frame_stride, order, scale, ow, oh, d_dst, dst_stride, dst_frame_stride);
+    if (rc) c->ev_used = ev0;
     else c->fail_stage = SRCNN_STAGE_NONE;
     return rc;
 }
@@ -352,6 +435,7 @@ int host_pipeline(Ctx* c, const uint8_t* src, int n, int w, int h, size_t src_st
     if (hit && !hit->exec && !hit->failed && is_pinned(src) && is_pinned(dst)) {
         // second sighting: capture.  Nothing below allocates, uploads or synchronises (tables, staging and planes exist).
         cudaGraph_t graph = nullptr;
+        const long long launches_before = c->launches;   // capturing enqueues nothing: the launch counter must not move
         cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
         if (e == cudaSuccess) {
             c->capturing = true;
@@ -363,6 +447,7 @@ int host_pipeline(Ctx* c, const uint8_t* src, int n, int w, int h, size_t src_st
             if (graph) cudaGraphDestroy(graph);
         }
         cudaGetLastError();
+        c->launches = launches_before;
         if (!hit->exec) hit->failed = true;   // run live from now on
     }
     StreamDrain drain{c};
@@ -466,6 +551,7 @@ int srcnn_create(srcnn_ctx** out, int device, int variant) {
     if (cudaDeviceSynchronize() != cudaSuccess) return bail(SRCNN_E_CUDA);
     if (const char* k = getenv("SRCNN_FUSE_MERGE")) c->fuse_merge = atoi(k) != 0;
     if (const char* k = getenv("SRCNN_TC2_SEG_OVH")) c->tc2_seg_ovh = std::max(0, std::min(64, atoi(k)));   // tuning aid
+    if (const char* k = getenv("SRCNN_BATCH_LAUNCH")) c->batch_launch = atoi(k) != 0;                        // A/B aid
     if (const char* k = getenv("SRCNN_GRAPHS")) c->use_graphs = atoi(k) != 0;                                // A/B aid
     if (const char* k = getenv("SRCNN_HOST_BANDS")) c->host_bands = std::max(1, std::min(64, atoi(k)));     // tuning aid
     *out = c;
@@ -529,6 +615,12 @@ extern "C" __attribute__((visibility("default"))) int srcnn_debug_set_tc2_seg_ov
 extern "C" __attribute__((visibility("default"))) int srcnn_debug_set_host_bands(srcnn_ctx* c, int bands) {
     if (!c || bands < 1 || bands > 64) return SRCNN_E_ARG;
     c->host_bands = bands;
+    return SRCNN_OK;
+}
+// test hook: a device-resident batch as one launch per stage and chunk (default) or frame by frame
+extern "C" __attribute__((visibility("default"))) int srcnn_debug_set_batch_launch(srcnn_ctx* c, int on) {
+    if (!c) return SRCNN_E_ARG;
+    c->batch_launch = on != 0;
     return SRCNN_OK;
 }
 // test hook: CUDA-graph replay of repeated host-buffer calls on / off; returns the number of instantiated graphs
@@ -639,12 +731,7 @@ int srcnn_process_batch_device(srcnn_ctx* c, const uint8_t* d_src, int n, int w,
     if (rc) return rc;
     if (n > 1 && (src_frame_stride < src_stride * (size_t)h || dst_frame_stride < dst_stride * (size_t)oh))
         return fail(c, SRCNN_E_ARG, "frame stride smaller than one frame");
-    for (int f = 0; f < n; f++) {
-        rc = process_rows(c, d_src + (size_t)f * src_frame_stride, w, h, src_stride, 0, h, order, scale, ow, oh, 0, oh,
-                          d_dst + (size_t)f * dst_frame_stride, dst_stride);
-        if (rc) return rc;
-    }
-    return SRCNN_OK;
+    return process_frames(c, d_src, n, w, h, src_stride, src_frame_stride, order, scale, ow, oh, d_dst, dst_stride, dst_frame_stride);
 }
 
 int srcnn_process_batch_host(srcnn_ctx* c, const uint8_t* src, int n, int w, int h, size_t src_stride,

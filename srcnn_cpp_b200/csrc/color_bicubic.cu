@@ -131,6 +131,8 @@ struct ResizeDev {
     size_t pitch;
     uint8_t* y16;      // tiled kernel: when set, Y goes to the padded FP16 plane (Planes::y16) INSTEAD of the u8 plane
     size_t pitch16;
+    // a batch of same-sized frames in one launch (blockIdx.z = frame): byte distance between consecutive frames
+    size_t src_frame, plane_frame, y16_frame;
     int plane_row0;
     const int* xofs;
     const short4* xcoef;
@@ -224,6 +226,9 @@ __global__ void __launch_bounds__(256, 5) k_color_bicubic_tiled(ResizeDev p) {  
     // once per sum instead of once per use in the vertical pass
     __shared__ __align__(16) float sH[3][kMaxSR][kTW];
 
+    const size_t fz = blockIdx.z;                       // frame of a batch
+    const uint8_t* const fsrc = p.src + fz * p.src_frame;
+    const size_t fplane = fz * p.plane_frame, fy16 = fz * p.y16_frame;
     const int dx0 = blockIdx.x * kTW;
     const int dy0 = p.row_begin + blockIdx.y * kTH;
     const int dx1 = min(dx0 + kTW, p.ow), dy1 = min(dy0 + kTH, p.row_end);
@@ -238,7 +243,7 @@ __global__ void __launch_bounds__(256, 5) k_color_bicubic_tiled(ResizeDev p) {  
         const int r = (int)(((unsigned)i * rcp20) >> 20), c = i - r * nsc;
         const int gy = clampi(sy_lo + r, 0, p.sh - 1) - p.src_row0;
         const int gx = clampi(sx_lo + c, 0, p.sw - 1);
-        const uint8_t* px = p.src + (size_t)gy * p.src_stride + 3 * (size_t)gx;
+        const uint8_t* px = fsrc + (size_t)gy * p.src_stride + 3 * (size_t)gx;
         int c0 = px[0], c1 = px[1], c2 = px[2];
         int B = p.swapRB ? c2 : c0, R = p.swapRB ? c0 : c2;
         int Y, Cr, Cb;
@@ -319,7 +324,7 @@ __global__ void __launch_bounds__(256, 5) k_color_bicubic_tiled(ResizeDev p) {  
                 const float sc = 1.0f / 4194304.0f;  // 2^-22, exact
                 const float b0 = __fmul_rn((float)cy.x, sc), b1 = __fmul_rn((float)cy.y, sc);
                 const float b2 = __fmul_rn((float)cy.z, sc), b3 = __fmul_rn((float)cy.w, sc);
-                const size_t o = (size_t)(dy - p.plane_row0) * p.pitch + dx;
+                const size_t o = fplane + (size_t)(dy - p.plane_row0) * p.pitch + dx;
                 const unsigned long long bb0 = f2_pack(b0, b0), bb1 = f2_pack(b1, b1), bb2 = f2_pack(b2, b2), bb3 = f2_pack(b3, b3);
 #pragma unroll
                 for (int pl = 0; pl < 3; pl++) {
@@ -344,7 +349,7 @@ __global__ void __launch_bounds__(256, 5) k_color_bicubic_tiled(ResizeDev p) {  
                             uint32_t a01 = (r0 | (r1 << 16)) | 0x64006400u, a23 = (r2 | (r3 << 16)) | 0x64006400u;
                             __half2 h01 = __hsub2(*reinterpret_cast<__half2*>(&a01), k1024), h23 = __hsub2(*reinterpret_cast<__half2*>(&a23), k1024);
                             const uint32_t w01 = *reinterpret_cast<uint32_t*>(&h01), w23 = *reinterpret_cast<uint32_t*>(&h23);
-                            uint8_t* o16 = p.y16 + (size_t)(dy - p.plane_row0) * p.pitch16 + 2 * (size_t)(dx + kY16Pad);
+                            uint8_t* o16 = p.y16 + fy16 + (size_t)(dy - p.plane_row0) * p.pitch16 + 2 * (size_t)(dx + kY16Pad);
                             *reinterpret_cast<uint2*>(o16) = make_uint2(w01, w23);
                             if (dx == 0) {            // replicated columns -8..-1 (conv1 reads Y[clamp(c-4)], src/srcnn.cpp:279)
                                 const uint32_t e = __byte_perm(w01, 0, 0x1010);
@@ -374,7 +379,7 @@ __global__ void __launch_bounds__(256, 5) k_color_bicubic_tiled(ResizeDev p) {  
                                                        __float2int_rn(hh[3][j]), cy, (dx + j) < p.simd_w);
                             if (pl == 0 && p.y16) {
                                 const unsigned short e = __half_as_ushort(__ushort2half_rn((unsigned short)r));
-                                unsigned short* q16 = reinterpret_cast<unsigned short*>(p.y16 + (size_t)(dy - p.plane_row0) * p.pitch16) + kY16Pad + dx + j;
+                                unsigned short* q16 = reinterpret_cast<unsigned short*>(p.y16 + fy16 + (size_t)(dy - p.plane_row0) * p.pitch16) + kY16Pad + dx + j;
                                 q16[0] = e;
                                 if (dx + j == 0)
                                     for (int k = 1; k <= kY16Pad; k++) q16[-k] = e;
@@ -403,6 +408,8 @@ int launch_color_bicubic(Ctx* c, const ResizeArgs& a) {
     p.y = a.pl.y; p.cr = a.pl.cr; p.cb = a.pl.cb;
     p.pitch = a.pl.pitch;
     p.y16 = nullptr; p.pitch16 = 0;
+    p.src_frame = a.src_frame_stride; p.plane_frame = a.pl.frame_stride; p.y16_frame = a.pl.frame_stride16;
+    const int nframes = std::max(1, a.nframes);
     p.plane_row0 = a.pl.row0;
     p.xofs = a.tx->d_ofs; p.xcoef = a.tx->d_coef;
     p.yofs = a.ty->d_ofs; p.ycoef = a.ty->d_coef;
@@ -431,17 +438,27 @@ int launch_color_bicubic(Ctx* c, const ResizeArgs& a) {
         if (a.tx->h_ofs[dx + 3] - a.tx->h_ofs[dx] > 4) p.quad_ok = 0;
     p.y16 = a.pl.y16; p.pitch16 = a.pl.pitch16;       // tiled kernel: the tcgen05 path's Y goes straight to the padded FP16 plane
     if (th) {
-        dim3 grid((a.ow + kTW - 1) / kTW, (rows + th - 1) / th);
+        dim3 grid((a.ow + kTW - 1) / kTW, (rows + th - 1) / th, nframes);   // a batch of frames is one launch
         if (th == 64) k_color_bicubic_tiled<64><<<grid, 256, 0, c->stream>>>(p);
         else k_color_bicubic_tiled<32><<<grid, 256, 0, c->stream>>>(p);
-    } else {
-        dim3 grid((a.ow + 31) / 32, (rows + 7) / 8);
-        k_color_bicubic_direct<<<grid, 256, 0, c->stream>>>(p);
+        c->launches++;
+        SRCNN_CUDA(c, cudaGetLastError());
+        return SRCNN_OK;
     }
-    c->launches++;
-    SRCNN_CUDA(c, cudaGetLastError());
-    if (!th && a.pl.y16)   // the direct kernel (strong down-scales) writes the u8 plane: the FP16 copy is a pass of its own there
-        return launch_y8_to_y16(c, a.pl.y, a.pl.pitch, a.ow, rows, a.pl.y16, a.pl.pitch16);
+    // the direct kernel (strong down-scales, rare): frame by frame; it writes the u8 plane, the FP16 copy is a pass of its own
+    for (int f = 0; f < nframes; f++) {
+        ResizeDev q = p;
+        q.src += (size_t)f * p.src_frame;
+        q.y += (size_t)f * p.plane_frame; q.cr += (size_t)f * p.plane_frame; q.cb += (size_t)f * p.plane_frame;
+        dim3 grid((a.ow + 31) / 32, (rows + 7) / 8);
+        k_color_bicubic_direct<<<grid, 256, 0, c->stream>>>(q);
+        c->launches++;
+        SRCNN_CUDA(c, cudaGetLastError());
+        if (a.pl.y16) {
+            int rc = launch_y8_to_y16(c, q.y, a.pl.pitch, a.ow, rows, a.pl.y16 + (size_t)f * a.pl.frame_stride16, a.pl.pitch16);
+            if (rc) return rc;
+        }
+    }
     return SRCNN_OK;
 }
 

@@ -69,6 +69,8 @@ struct Planes {
     uint8_t* yout = nullptr;
     size_t pitch = 0;
     int row0 = 0, rows = 0;
+    // a batch of frames: frame f's planes start f * frame_stride (u8 planes) / f * frame_stride16 (FP16 plane) bytes further
+    size_t frame_stride = 0, frame_stride16 = 0;
 };
 
 // row-walking kernel: the cached cut of a launch's row steps over its pipelines (srcnn_tc2.cu, tc2_partition)
@@ -118,6 +120,7 @@ struct Ctx {
     bool fuse_merge = false;         // row-walking kernel: merge + YCrCb->BGR in its last epilogue instead of the K-C launch
                                      // (SRCNN_FUSE_MERGE=1; byte-identical, but 0.236 vs 0.214 ms per 4K frame: off by default)
     Tc2Partition tc2_part;
+    bool batch_launch = true;        // device-resident batches: one launch per stage and chunk of frames (SRCNN_BATCH_LAUNCH=0: frame by frame)
     int host_bands = 8;              // host-buffer pipeline: most sub-bands a single frame is cut into (SRCNN_HOST_BANDS)
     int tc2_seg_ovh = 12;            // cost of opening a segment, in row steps (SRCNN_TC2_SEG_OVH; 0 = cut into equal row counts)
     int* d_guard = nullptr;          // device-side watchdog flag (mapped pinned)
@@ -172,6 +175,8 @@ struct ResizeArgs {
     Planes pl;            // destination planes (pl.row0 = output row stored at plane row 0)
     const TapTable* tx;
     const TapTable* ty;
+    int nframes = 1;      // same-sized frames in one launch, src_frame_stride / pl.frame_stride apart
+    size_t src_frame_stride = 0;
 };
 int launch_color_bicubic(Ctx* c, const ResizeArgs& a);
 
@@ -210,6 +215,9 @@ struct CnnArgs {
     uint8_t* bgr = nullptr;
     size_t bgr_stride = 0;
     int order = 0;
+    // a batch of frames in one launch (row-walking tcgen05 kernel; not with the fused merge): frames are more strips
+    int nframes = 1;
+    size_t y16_frame_stride = 0, out_frame_stride = 0;
 };
 int launch_cnn_fp32(Ctx* c, const CnnArgs& a, float* act2_out /* optional full act2 dump, may be null */);
 int fp32_prepare(Ctx* c);    // uploads the parameters to the device's constant bank (once per device and process)

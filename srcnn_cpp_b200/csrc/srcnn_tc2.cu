@@ -317,7 +317,9 @@ struct Params {
     int swap_rb;           // 1: R,G,B byte order
     const uint8_t* wimg;   // packed FP16 operand image (kWeightBytes)
     float b3;              // conv3 bias (src/convdata.h:979), added in FP32 by the last epilogue
-    long long total;       // strips x (out_end - out_begin) row steps
+    int nstrips;           // strips per frame; a batch of frames is nframes x nstrips strips, frame-major
+    size_t y16_frame, out_frame;   // byte distance between consecutive frames' FP16 Y planes / Y' planes
+    long long total;       // frames x strips x (out_end - out_begin) row steps
     long long bounds[kMaxWorkers + 1];   // pipeline w walks row steps [bounds[w], bounds[w+1]) of the strip-major order (tc2_partition)
     int* guard;
     unsigned long long watchdog_ns;   // time allowance of this launch (0 = no deadline)
@@ -524,8 +526,10 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
 
     while (lin < lin_end) {
         // ---- one segment: strip `strip`, output rows [ra, rb) ----
-        const int strip = (int)(lin / Hb);
-        const int rfirst = (int)(lin - (long long)strip * Hb);
+        const int gstrip = (int)(lin / Hb);                 // strip of the whole batch
+        const int rfirst = (int)(lin - (long long)gstrip * Hb);
+        const int frame = gstrip / p.nstrips, strip = gstrip - frame * p.nstrips;
+        (void)frame;
         const int cnt = (int)min((long long)(Hb - rfirst), lin_end - lin);
         lin += cnt;
         const int xs = strip * kStripCols;
@@ -629,7 +633,7 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
             const uint32_t tile_off = 4u + 8u * (uint32_t)odd;      // byte offset of tile column 0 (image column xs - 6) in a staged row
             // The plane row of ring row q is clamp(clamp(ta-4+q, 0, H-1) - row0, 0, rows-1)
             auto plane_row = [&](int q) { return min(max(min(max(ta - 4 + q, 0), H - 1) - p.row0, 0), p.rows - 1); };
-            const uint8_t* ysrc = p.y16 + 2 * (size_t)(xs - 4 * odd);
+            const uint8_t* ysrc = p.y16 + (size_t)frame * p.y16_frame + 2 * (size_t)(xs - 4 * odd);
             const uint32_t ybase = ycount;                          // staged rows before this segment: slot and phase run on
             auto issue_row = [&](int q) {                           // one lane
                 const uint32_t k = ybase + (uint32_t)q, sl = k & (kYSlots - 1);
@@ -736,7 +740,7 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
                 for (int n = 0; n < 5; n++) acc[k][n] = 0.f;
             // rows are stored in order ra, ra+1, ...
             uint8_t* outp = FUSED ? p.bgr + (size_t)(ra - p.out_begin) * p.bgr_stride + (size_t)3 * (col_ok ? x : 0)
-                                  : p.out + (size_t)(ra - p.row0) * p.out_pitch + x;
+                                  : p.out + (size_t)frame * p.out_frame + (size_t)(ra - p.row0) * p.out_pitch + x;
             const uint8_t* crp = FUSED ? p.cr + (size_t)(ra - p.row0) * p.pitch + (col_ok ? x : 0) : nullptr;
             const uint8_t* cbp = FUSED ? p.cb + (size_t)(ra - p.row0) * p.pitch + (col_ok ? x : 0) : nullptr;
             E3Ctx cx{p, hx_s + 4 * tp, ctr + 4 * (uint32_t)(tp >> 5), bars, tml, tp, pipe, ta, tb, ra, rb, col_ok, first_seg, warp0, leader};
@@ -973,7 +977,12 @@ int launch_cnn_tc2(Ctx* c, const CnnArgs& a0) {
     p.swap_rb = a.order == SRCNN_ORDER_RGB ? 1 : 0;
     p.wimg = (const uint8_t*)c->d_tc2_weights;
     p.b3 = c->b3;
-    const int nstrips = (a.W + kStripCols - 1) / kStripCols;
+    const int nframes = std::max(1, a.nframes);
+    if (nframes > 1 && a.bgr) return fail(c, SRCNN_E_ARG, "fused merge does not take a batch of frames");
+    const int nstrips1 = (a.W + kStripCols - 1) / kStripCols;
+    const int nstrips = nstrips1 * nframes;
+    p.nstrips = nstrips1;
+    p.y16_frame = a.y16_frame_stride; p.out_frame = a.out_frame_stride;
     p.total = (long long)nstrips * (a.out_end - a.out_begin);
     p.guard = c->d_guard;
     p.dbg = nullptr;

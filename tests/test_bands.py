@@ -32,3 +32,34 @@ def test_bands_equal_whole(engine, variant_name, w, h, scale, nb):
     finally:
         engine.set_variant(S.VARIANT_TC)
     assert torch.equal(whole, banded)
+
+
+@pytest.mark.parametrize("w,h,scale,n", [(70, 90, 1.5, 5), (130, 64, 2.0, 3), (64, 48, 3.0, 4), (96, 80, 0.5, 3)])
+def test_batch_in_one_launch_equals_frame_by_frame(engine, w, h, scale, n):
+    """srcnn_process_batch_device runs a chunk of frames as ONE launch per stage (frames = a grid dimension of the colour+bicubic
+    kernel, more strips of the row-walking kernel's work list, one tall image for the merge kernel): bit-identical to calling
+    the frames one by one, also when the caller's result frames are not contiguous, and for a geometry the tiled kernel does not
+    take (down-scale: direct kernel + separate FP16 pass)."""
+    import ctypes as C
+    import torch
+    import srcnn_cpp_b200 as S
+    rng = np.random.default_rng(w + h + n)
+    frames = np.stack([natural_like(rng, h, w) for _ in range(n)])
+    ow, oh = S.out_dims(w, h, scale)
+    d = torch.from_numpy(frames).to("cuda:0")
+    one = torch.zeros((n, oh, ow, 3), dtype=torch.uint8, device="cuda:0")
+    for k in range(n):
+        engine.process_device(d[k], scale, one[k])
+    batch = torch.zeros_like(one)
+    engine.process_batch_device(d, scale, batch)
+    gappy = torch.zeros((n, oh + 3, ow, 3), dtype=torch.uint8, device="cuda:0")[:, :oh]     # frame stride != rows x row stride
+    engine.process_batch_device(d, scale, gappy)
+    engine.L.srcnn_debug_set_batch_launch.argtypes = [C.c_void_p, C.c_int]
+    engine.L.srcnn_debug_set_batch_launch(engine.ctx, 0)
+    try:
+        loop = torch.zeros_like(one)
+        engine.process_batch_device(d, scale, loop)
+    finally:
+        engine.L.srcnn_debug_set_batch_launch(engine.ctx, 1)
+    engine.sync()
+    assert torch.equal(batch, one) and torch.equal(gappy, one) and torch.equal(loop, one)

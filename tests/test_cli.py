@@ -91,3 +91,23 @@ def test_jpeg_in_and_out(tmp_path, oracle):
     want = oracle.pipeline(cv2.imread(src), 2.0)
     mse = np.mean((out.astype(np.float64) - want.astype(np.float64)) ** 2)
     assert 10 * np.log10(255.0 ** 2 / mse) > 30.0
+
+
+@pytest.mark.gpu
+def test_devices_option_splits_the_image_into_bands(tmp_path):
+    """--devices=a,b,.. : one row band per listed device through srcnn_mgpu_process_banded_host; same bytes as one device
+    (a device may be listed twice, so this runs on a one-GPU box too)."""
+    import cv2
+    src = os.path.join(ROOT, "tests", "golden", "butterfly.png")
+    gold = cv2.imread(os.path.join(ROOT, "tests", "golden", "butterfly-srcnn.png"))
+    one, many = str(tmp_path / "one.png"), str(tmp_path / "many.png")
+    assert _run("--scale=1.5", "--variant=fp32", "--noverbose", src, one).returncode == 0
+    r = _run("--scale=1.5", "--variant=fp32", "--devices=0,0,0", src, many)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert np.array_equal(cv2.imread(many), cv2.imread(one)) and np.array_equal(cv2.imread(many), gold)
+    r = _run("--scale=1.5", "--devices=all", "--noverbose", src, many)
+    assert r.returncode == 0
+    d = np.abs(cv2.imread(many).astype(np.int16) - gold.astype(np.int16))
+    assert d.max() <= 2 and (d <= 1).mean() >= 0.999
+    r = _run("--devices=0,99", "--noverbose", src, many)      # a device that does not exist
+    assert r.returncode != 0

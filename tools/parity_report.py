@@ -164,7 +164,7 @@ def main():
         src = base.repeat_interleave(64, 0).repeat_interleave(64, 1)
         src += torch.randint(0, 24, (SH, SW, 3), dtype=torch.uint8, device="cuda", generator=gen)
         del base
-        wins = [(4096 * k - 128, 5000 * k, 256) for k in range(1, 8)] + [(0, 0, 256), (0, SW - 256, 256), (SH - 256, 0, 256), (SH - 256, SW - 256, 256)]
+        wins = [(4096 * k - 128, 4000 * k, 256) for k in range(1, 8)] + [(0, 0, 256), (0, SW - 256, 256), (SH - 256, 0, 256), (SH - 256, SW - 256, 256)]
         rep.append(windows("cfg4 32768^2 -> 65536^2 x2", src, 2.0, wins,
                            "whole image on one GPU (bands == whole is pinned bit for bit by tests/test_large_configs.py and tests/test_mgpu.py); 11 source windows of 256^2: across each of the 7 seams of an 8-band split, and the 4 corners"))
         print(json.dumps(rep[-1]), flush=True)
