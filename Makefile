@@ -10,7 +10,7 @@ CSRC := srcnn_cpp_b200/csrc
 OBJ := build/obj
 LIB := srcnn_cpp_b200/libsrcnn_b200.so
 WEIGHTS := $(abspath srcnn_cpp_b200/data/srcnn_weights.bin)
-CU := api mgpu color_bicubic srcnn_fp32 srcnn_tc2 fraw_resize
+CU := api mgpu jpeg_stream color_bicubic srcnn_fp32 srcnn_tc2 fraw_resize
 OBJS := $(addprefix $(OBJ)/,$(addsuffix .o,$(CU))) $(OBJ)/weights_blob.o $(OBJ)/libsrcnn.o
 
 all: $(LIB) bin/srcnn oracle
@@ -35,7 +35,7 @@ bin/srcnn: srcnn_cpp_b200/cli/srcnn_main.cpp srcnn_cpp_b200/cli/image_io.cpp src
 	    -ldl -lrt -lz -lpthread -Wl,-rpath,'$$ORIGIN/../srcnn_cpp_b200'
 
 $(LIB): $(OBJS)
-	$(NVCC) $(ARCH) -shared -ccbin $(HOSTCXX) -Xcompiler -fPIC -o $@ $(OBJS) -lcuda
+	$(NVCC) $(ARCH) -shared -ccbin $(HOSTCXX) -Xcompiler -fPIC -o $@ $(OBJS) -lnvjpeg_static -lculibos -lcuda
 
 oracle:
 	$(MAKE) -C oracle

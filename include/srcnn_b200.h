@@ -172,6 +172,20 @@ int srcnn_mgpu_process_banded_device(srcnn_mgpu* m, const uint8_t* const* d_src,
  * srcnn_mgpu_device_count() doubles. */
 int srcnn_mgpu_last_timing(srcnn_mgpu* m, double* ms_per_worker, double* wall_ms);
 
+/* ---- stream ingest: JPEG frames in, JPEG frames out ----------------------------------
+ * The reference decodes one file before and encodes one after its timed region (cv::imread / cv::imwrite,
+ * src/srcnn.cpp:462,670).  For a stream of same-sized frames: nvJPEG decode of frame i+1, the kernels of frame i
+ * and the nvJPEG encode of frame i-1 overlap on three streams; pixels never visit host memory.  out[i] is
+ * allocated by the library (release with srcnn_jpeg_free); quality 95 + 4:2:0 = cv::imwrite's defaults.  File
+ * codecs are outside the parity contract. */
+typedef struct srcnn_jpeg_stream srcnn_jpeg_stream;
+int srcnn_jpeg_stream_create(srcnn_jpeg_stream** out, srcnn_ctx* ctx, int quality);
+int srcnn_jpeg_stream_destroy(srcnn_jpeg_stream* s);
+const char* srcnn_jpeg_stream_last_error(srcnn_jpeg_stream* s);
+int srcnn_jpeg_stream_process(srcnn_jpeg_stream* s, const uint8_t* const* jpegs, const size_t* sizes, int n, float scale,
+                              uint8_t** out, size_t* out_sizes, int* out_w, int* out_h);
+void srcnn_jpeg_free(uint8_t* p);
+
 /* ---- stages (device pointers; enqueued on the context stream) ------------------------------------ */
 /* cvtColor + split + 3x resize (src/srcnn.cpp:509,540,570-583): BGR8 -> three u8 planes of ow x oh. */
 int srcnn_stage_color_bicubic_device(srcnn_ctx* ctx, const uint8_t* d_src, int w, int h, size_t src_stride,

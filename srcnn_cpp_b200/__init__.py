@@ -43,6 +43,7 @@ ABI_SYMBOLS = [
     "srcnn_mgpu_create", "srcnn_mgpu_destroy", "srcnn_mgpu_device_count", "srcnn_mgpu_context", "srcnn_mgpu_last_error",
     "srcnn_mgpu_band_plan", "srcnn_mgpu_process_batch_host", "srcnn_mgpu_process_banded_host",
     "srcnn_mgpu_process_batch_device", "srcnn_mgpu_process_banded_device", "srcnn_mgpu_last_timing",
+    "srcnn_jpeg_stream_create", "srcnn_jpeg_stream_destroy", "srcnn_jpeg_stream_last_error", "srcnn_jpeg_stream_process", "srcnn_jpeg_free",
 ]
 
 
@@ -119,6 +120,13 @@ def load_library():
                                                   C.POINTER(vp), sz, sz]
     L.srcnn_mgpu_process_banded_device.argtypes = [vp, C.POINTER(vp), C.c_int, C.c_int, sz, C.c_int, C.c_float, C.POINTER(vp), sz]
     L.srcnn_mgpu_last_timing.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.srcnn_jpeg_stream_create.argtypes = [C.POINTER(vp), vp, C.c_int]
+    L.srcnn_jpeg_stream_destroy.argtypes = [vp]
+    L.srcnn_jpeg_stream_last_error.restype = C.c_char_p
+    L.srcnn_jpeg_stream_last_error.argtypes = [vp]
+    L.srcnn_jpeg_stream_process.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(sz), C.c_int, C.c_float, C.POINTER(vp), C.POINTER(sz), i32p, i32p]
+    L.srcnn_jpeg_free.restype = None
+    L.srcnn_jpeg_free.argtypes = [vp]
     _lib = L
     return L
 
@@ -446,3 +454,43 @@ class MultiEngine:
         sref = next(t for t in src_bands if t is not None)
         dref = next(t for t in dst_bands if t is not None)
         self._check(self.L.srcnn_mgpu_process_banded_device(self.h, ps, w, h, sref.stride(0), order, C.c_float(scale), pd, dref.stride(0)))
+
+
+class JpegStream:
+    """srcnn_jpeg_stream: a stream of same-sized JPEG frames through decode -> whole path -> encode, all on the device."""
+
+    def __init__(self, engine, quality=95):
+        self.L, self.engine = engine.L, engine
+        self.h = C.c_void_p()
+        rc = self.L.srcnn_jpeg_stream_create(C.byref(self.h), engine.ctx, int(quality))
+        if rc != OK:
+            self.h = None
+            raise SrcnnError(rc, self.L.srcnn_strerror(rc).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.srcnn_jpeg_stream_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def process(self, jpegs, scale):
+        """jpegs: list of bytes objects -> (list of bytes objects, (ow, oh))"""
+        n = len(jpegs)
+        arr = (C.c_char_p * n)(*jpegs)
+        sizes = (C.c_size_t * n)(*[len(j) for j in jpegs])
+        out = (C.c_void_p * n)()
+        osz = (C.c_size_t * n)()
+        ow, oh = C.c_int(), C.c_int()
+        rc = self.L.srcnn_jpeg_stream_process(self.h, arr, sizes, n, C.c_float(scale), out, osz, C.byref(ow), C.byref(oh))
+        if rc != OK:
+            raise SrcnnError(rc, (self.L.srcnn_jpeg_stream_last_error(self.h) or b"").decode())
+        res = []
+        for i in range(n):
+            res.append(C.string_at(out[i], osz[i]))
+            self.L.srcnn_jpeg_free(out[i])
+        return res, (ow.value, oh.value)

@@ -301,7 +301,9 @@ void drop_graphs(Ctx* c) {
 // into the compute stream; does not wait.  Identical whether the streams are live or being captured into a CUDA graph.
 static int enqueue_chunk(Ctx* c, const uint8_t* src, int f0, int m, int w, int h, size_t src_stride, size_t src_frame_stride, int order,
                          float scale, int ow, int oh, int R0, int R1, uint8_t* dst, size_t dst_stride, size_t dst_frame_stride,
-                         const TapTable* ty, int S0, int S1, int bands, size_t s_row, size_t d_row, size_t s_frame, size_t d_frame) {
+                         const TapTable* ty, int S0, int S1, const std::vector<int>& edges, int group, size_t s_row, size_t d_row, size_t s_frame,
+                         size_t d_frame) {
+    const int bands = (int)edges.size() - 1;
     int rc;
     uint8_t* ds = (uint8_t*)c->src_buf.p;
     uint8_t* dd = (uint8_t*)c->dst_buf.p;
@@ -326,12 +328,56 @@ static int enqueue_chunk(Ctx* c, const uint8_t* src, int f0, int m, int w, int h
     SRCNN_CUDA(c, cudaEventRecord(ev_start, c->stream));
     SRCNN_CUDA(c, cudaStreamWaitEvent(c->s_in, ev_start, 0));
     SRCNN_CUDA(c, cudaStreamWaitEvent(c->s_out, ev_start, 0));
+    if (bands == 1 && m > 1) {
+        // A batch of whole frames: groups of frames travel together -- one copy in, ONE launch per stage (process_frames: no
+        // per-frame pipeline fill / drain in the fused kernel), one copy out -- sized so that a group's result is >= 64 MB:
+        // large copies keep the PCIe link busy, and the next group's kernels still hide behind this group's D2H.
+        const bool rows_tight_in = src_stride == (size_t)w * 3 && s_row == (size_t)w * 3;      // a frame is one contiguous run of bytes
+        const bool rows_tight_out = dst_stride == (size_t)ow * 3 && d_row == (size_t)ow * 3;
+        for (int g0 = 0; g0 < m; g0 += group) {
+            const int g = std::min(group, m - g0);
+            const uint8_t* hsrc = src + (size_t)(f0 + g0) * src_frame_stride;
+            uint8_t* hdst = dst + (size_t)(f0 + g0) * dst_frame_stride;
+            cudaEvent_t ev_in, ev_done;
+            if ((rc = event_at(ei++, &ev_in))) return rc;
+            if (rows_tight_in) {   // frames are the "rows" of one 2-D copy
+                SRCNN_CUDA(c, cudaMemcpy2DAsync(ds + (size_t)g0 * s_frame, s_frame, hsrc + (size_t)S0 * src_stride, src_frame_stride,
+                                                (size_t)(S1 - S0) * s_row, g, cudaMemcpyHostToDevice, c->s_in));
+            } else {
+                for (int f = 0; f < g; f++)
+                    SRCNN_CUDA(c, cudaMemcpy2DAsync(ds + (size_t)(g0 + f) * s_frame, s_row, hsrc + (size_t)f * src_frame_stride + (size_t)S0 * src_stride,
+                                                    src_stride, (size_t)w * 3, S1 - S0, cudaMemcpyHostToDevice, c->s_in));
+            }
+            SRCNN_CUDA(c, cudaEventRecord(ev_in, c->s_in));
+            SRCNN_CUDA(c, cudaStreamWaitEvent(c->stream, ev_in, 0));
+            if (R0 == 0 && R1 == oh) {
+                rc = process_frames(c, ds + (size_t)g0 * s_frame, g, w, h, s_row, s_frame, order, scale, ow, oh, dd + (size_t)g0 * d_frame, d_row, d_frame);
+                if (rc) return rc;
+            } else {
+                for (int f = 0; f < g; f++) {
+                    rc = process_rows(c, ds + (size_t)(g0 + f) * s_frame, w, h, s_row, S0, S1, order, scale, ow, oh, R0, R1, dd + (size_t)(g0 + f) * d_frame, d_row);
+                    if (rc) return rc;
+                }
+            }
+            if ((rc = event_at(ei++, &ev_done))) return rc;
+            SRCNN_CUDA(c, cudaEventRecord(ev_done, c->stream));
+            SRCNN_CUDA(c, cudaStreamWaitEvent(c->s_out, ev_done, 0));
+            if (rows_tight_out) {
+                SRCNN_CUDA(c, cudaMemcpy2DAsync(hdst, dst_frame_stride, dd + (size_t)g0 * d_frame, d_frame, (size_t)rows * d_row, g,
+                                                cudaMemcpyDeviceToHost, c->s_out));
+            } else {
+                for (int f = 0; f < g; f++)
+                    SRCNN_CUDA(c, cudaMemcpy2DAsync(hdst + (size_t)f * dst_frame_stride, dst_stride, dd + (size_t)(g0 + f) * d_frame, d_row, (size_t)ow * 3, rows,
+                                                    cudaMemcpyDeviceToHost, c->s_out));
+            }
+        }
+    } else
     for (int f = 0; f < m; f++) {
         const uint8_t* hsrc = src + (size_t)(f0 + f) * src_frame_stride;
         uint8_t* hdst = dst + (size_t)(f0 + f) * dst_frame_stride;
         int copied = S0;   // source rows [S0, copied) of this frame are on their way to the device
         for (int bi = 0; bi < bands; bi++) {
-            const int r0 = R0 + (int)((long long)rows * bi / bands), r1 = R0 + (int)((long long)rows * (bi + 1) / bands);
+            const int r0 = edges[bi], r1 = edges[bi + 1];
             const int s_hi = bi + 1 < bands ? src_hi(r1) : S1;
             if (s_hi > copied) {
                 cudaEvent_t ev_in;
@@ -379,30 +425,49 @@ int host_pipeline(Ctx* c, const uint8_t* src, int n, int w, int h, size_t src_st
     // device staging: tight rows, 256-byte aligned frames; only the rows this call needs
     const size_t s_row = align_up((size_t)w * 3, 4), d_row = align_up((size_t)ow * 3, 4);
     const size_t s_frame = align_up(s_row * (size_t)(S1 - S0), 256), d_frame = align_up(d_row * (size_t)(R1 - R0), 256);
-    // frames in flight are bounded so staging stays modest (<= ~1 GiB of output; one frame may be larger)
-    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n, ((size_t)1 << 30) / d_frame));
+    // frames in flight are bounded so staging stays modest (<= 4 GiB of output; one frame may be larger).  Chunks are separated by
+    // a full drain of the pipeline, so the bound is generous: 180 GB of HBM is not the scarce resource here.
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n, ((size_t)4 << 30) / d_frame));
     if ((rc = ensure(c, c->src_buf, s_frame * chunk))) return rc;
     if ((rc = ensure(c, c->dst_buf, d_frame * chunk))) return rc;
     if (!c->s_in) {
         SRCNN_CUDA(c, cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
         SRCNN_CUDA(c, cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
     }
-    // A single large frame is cut into sub-bands of >= 512 output rows (at most c->host_bands, default 8); each sub-band's
-    // source rows are copied in separately, so the first one computes after a fraction of the H2D and the D2H stream (the
-    // PCIe-bound leg) starts early and never idles.  Measured at 1080p -> 4K: 4 bands 0.587 ms, 8 bands 0.592 ms, 12 bands
-    // 0.72 ms (per-band launch overhead of the persistent kernel takes over).  Very tall bands (a gigapixel image) are cut
-    // so that a sub-band's planes stay below ~256 MB.
+    // A single large frame is cut into sub-bands; each sub-band's source rows are copied in separately, so the first one computes
+    // after a fraction of the H2D and the D2H stream (the PCIe-bound leg: 4x the H2D bytes at x2) starts early and never idles.
+    // The bands GROW: a band's kernels (~25 us of launches and pipeline fill + ~0.09 us per 4K row) only have to finish before
+    // the previous band's D2H (~0.21 us per row) does, so a short first band starts the D2H early and longer later bands
+    // keep the per-band overhead of the persistent kernel small (equal bands: 8 x 47 us of fused kernel for a frame that takes
+    // 147 us whole).  Very tall bands (a gigapixel image) are cut into equal pieces whose planes stay below ~256 MB.
     const int rows = R1 - R0;
-    int bands = 1;
+    std::vector<int> edges{R0};
     if (n == 1 && rows >= 1024) {
-        bands = std::min(c->host_bands, rows / 512);
         const long long by_mem = ((long long)rows * (long long)ow * 4 + (256ll << 20) - 1) / (256ll << 20);
-        bands = (int)std::max<long long>(bands, std::min<long long>(by_mem, rows / 64));
+        if (by_mem > c->host_bands) {
+            const int nb = (int)std::min<long long>(by_mem, rows / 64);
+            for (int bi = 1; bi < nb; bi++) edges.push_back(R0 + (int)((long long)rows * bi / nb));
+        } else if (c->host_bands > 1) {
+            double len = std::max(256.0, (double)rows / c->host_bands);
+            int pos = R0;
+            while ((int)edges.size() < c->host_bands) {
+                const int take = (int)len;
+                if (R1 - (pos + take) < take / 2) break;      // the rest joins the last band
+                pos += take;
+                edges.push_back(pos);
+                len *= 1.45;
+            }
+        }
     }
-    {   // the planes of the tallest sub-band, allocated before anything is enqueued or captured
+    edges.push_back(R1);
+    const int bands = (int)edges.size() - 1;
+    int tallest = 0;
+    for (int bi = 0; bi < bands; bi++) tallest = std::max(tallest, edges[bi + 1] - edges[bi]);
+    // frames of a batch travel in groups whose result is >= 64 MB (see enqueue_chunk)
+    const int group = (int)std::max<size_t>(1, std::min<size_t>(16, ((size_t)64 << 20) / std::max<size_t>(1, (size_t)ow * 3 * (size_t)rows) + 1));
+    {   // the planes of the tallest sub-band / of a group of frames, allocated before anything is enqueued or captured
         Planes pl;
-        const int tallest = (rows + bands - 1) / bands + 12;
-        if ((rc = carve_planes(c, ow, std::min(tallest, oh), 0, &pl))) return rc;
+        if ((rc = carve_planes(c, ow, std::min(tallest + 12, oh), 0, &pl, (bands == 1 && n > 1) ? std::min(group, n) : 1))) return rc;
     }
 
     // ---- CUDA-graph replay.  A call that repeats an earlier one exactly (same buffers, same geometry: a stream of frames through
@@ -440,7 +505,7 @@ int host_pipeline(Ctx* c, const uint8_t* src, int n, int w, int h, size_t src_st
         if (e == cudaSuccess) {
             c->capturing = true;
             rc = enqueue_chunk(c, src, 0, n, w, h, src_stride, src_frame_stride, order, scale, ow, oh, R0, R1, dst, dst_stride,
-                               dst_frame_stride, ty, S0, S1, bands, s_row, d_row, s_frame, d_frame);
+                               dst_frame_stride, ty, S0, S1, edges, group, s_row, d_row, s_frame, d_frame);
             e = cudaStreamEndCapture(c->stream, &graph);
             c->capturing = false;
             if (rc == SRCNN_OK && e == cudaSuccess && graph && cudaGraphInstantiate(&hit->exec, graph, 0) != cudaSuccess) hit->exec = nullptr;
@@ -461,7 +526,7 @@ int host_pipeline(Ctx* c, const uint8_t* src, int n, int w, int h, size_t src_st
         const int m = std::min(chunk, n - f0);
         const long long l0 = c->launches;
         rc = enqueue_chunk(c, src, f0, m, w, h, src_stride, src_frame_stride, order, scale, ow, oh, R0, R1, dst, dst_stride,
-                           dst_frame_stride, ty, S0, S1, bands, s_row, d_row, s_frame, d_frame);
+                           dst_frame_stride, ty, S0, S1, edges, group, s_row, d_row, s_frame, d_frame);
         if (rc) return rc;
         if (graphable && f0 == 0)
             for (auto& g : c->graphs)
