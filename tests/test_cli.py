@@ -47,7 +47,7 @@ def test_cfg1_butterfly_via_cli_is_bit_exact(tmp_path):
     assert r.returncode == 0 and r.stdout == ""
     out = cv2.imread(str(tmp_path / "b_resized.png"))
     d = np.abs(out.astype(np.int16) - gold.astype(np.int16))
-    assert d.max() <= 3 and (d <= 1).mean() >= 0.999
+    assert d.max() <= 2 and (d <= 1).mean() >= 0.999
 
 
 @pytest.mark.gpu
@@ -68,7 +68,7 @@ def test_process_srcnn_library_entry(oracle):
     got = np.ctypeslib.as_array((C.c_uint8 * sz.value).from_address(out.value)).reshape(40, 52, 3)
     want = oracle.pipeline(bgr, 2.0)[:, :, ::-1]
     d = np.abs(got.astype(np.int16) - want.astype(np.int16))
-    assert d.max() <= 3 and (d <= 1).mean() >= 0.995
+    assert d.max() <= 2 and (d <= 1).mean() >= 0.999
     # 4-channel input keeps 4 channels (src/test.cpp: outsz uses d)
     rgba = np.dstack([rgb, np.full((20, 26), 200, np.uint8)])
     assert fn(np.ascontiguousarray(rgba).ctypes.data, 26, 20, 4, C.c_float(2.0), C.byref(out), C.byref(sz)) == 0

@@ -186,7 +186,7 @@ def test_golden_end_to_end_host_api(engine, golden, variant_name):
         assert np.array_equal(out, dst)          # byte for byte == Pictures/butterfly-srcnn.png
     else:
         st = diff_stats(out, dst)
-        assert st["max"] <= 3 and st["le1"] >= TC_MIN_LE1, st   # BGR after colour-back of a <=2 LSB Y'
+        assert st["max"] <= TC_MAX_ABS and st["le1"] >= TC_MIN_LE1, st   # BGR inherits the bound of Y (every channel moves by at most |dY|)
 
 
 @pytest.mark.parametrize("w,h,scale", [(96, 64, 2.0), (37, 29, 1.5), (50, 41, 3.0), (31, 45, 4.0)])

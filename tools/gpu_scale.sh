@@ -1,7 +1,8 @@
 #!/bin/bash
 # Multi-GPU round on ONE box with NG GPUs (gpurun --gpus NG): bench lines of every configuration at N = NG, one rank per GPU
-# (torchrun) and through the in-library driver (--mgpu, one process); at NG = 8 also the host-buffer knobs.
-NG=${1:-8}
+# (torchrun) and through the in-library driver (--mgpu, one process).  usage: gpu_scale.sh NG [cfgs...]
+NG=${1:-8}; shift
+CFGS=${@:-cfg2 cfg3 cfg4 cfg5}
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
 run() { name=$1; shift; timeout 900 "$@" > gpurun_out/$name.log 2>&1; echo "exit=$?" >> gpurun_out/$name.log; python - "$name" <<'PY'
@@ -14,16 +15,8 @@ else:
     print(sys.argv[1], open('gpurun_out/%s.log'%sys.argv[1]).read()[-1200:])
 PY
 }
-nvidia-smi -L | head -8; nproc; free -g | head -2
-run b_cfg2_n$NG python bench.py --no-cpu --gpus $NG
-run b_cfg3_n$NG python bench.py --config cfg3 --no-cpu --gpus $NG
-run b_cfg4_n$NG python bench.py --config cfg4 --no-cpu --gpus $NG
-run b_cfg5_n$NG python bench.py --config cfg5 --no-cpu --gpus $NG
-run b_cfg3_n${NG}_mgpu python bench.py --config cfg3 --no-cpu --gpus $NG --mgpu
-run b_cfg4_n${NG}_mgpu python bench.py --config cfg4 --no-cpu --gpus $NG --mgpu
-run b_cfg5_n${NG}_mgpu python bench.py --config cfg5 --no-cpu --gpus $NG --mgpu
-if [ "$NG" = "8" ]; then
-  SRCNN_HOST_BANDS=2 run b_cfg2_n8_bands2 python bench.py --no-cpu --gpus 8 --steps 20
-  SRCNN_HOST_BANDS=4 run b_cfg2_n8_bands4 python bench.py --no-cpu --gpus 8 --steps 20
-  SRCNN_GRAPHS=0 run b_cfg2_n8_nograph python bench.py --no-cpu --gpus 8 --steps 20
-fi
+nvidia-smi -L | wc -l; nproc
+for c in $CFGS; do
+  run b_${c}_n$NG python bench.py --config $c --no-cpu --gpus $NG
+  if [ "$c" != "cfg2" ] && [ -z "$NOMGPU" ]; then run b_${c}_n${NG}_mgpu python bench.py --config $c --no-cpu --gpus $NG --mgpu; fi
+done
