@@ -477,9 +477,9 @@ int host_pipeline(Ctx* c, const uint8_t* src, int n, int w, int h, size_t src_st
     const bool graphable = c->use_graphs && !c->profiling && chunk >= n && bands * n <= 256;
     if (graphable) {
         PipeKey key{src, dst, n, w, h, src_stride, src_frame_stride, order, scale, R0, R1, dst_stride, dst_frame_stride, c->variant,
-                    (int)c->fuse_merge, c->host_bands, 0, 0, c->tc2_seg_ovh, (void*)c->stream};
+                    (int)c->fuse_merge, c->host_bands, c->tc2_seg_ovh, (void*)c->stream};
         for (auto& g : c->graphs)
-            if (memcmp(&g.key, &key, sizeof(key)) == 0) hit = &g;
+            if (g.key == key) hit = &g;
         if (!hit) {
             if (c->graphs.size() >= 8) {   // forget the least recently used
                 size_t v = 0;
@@ -489,7 +489,6 @@ int host_pipeline(Ctx* c, const uint8_t* src, int n, int w, int h, size_t src_st
                 c->graphs.erase(c->graphs.begin() + v);
             }
             PipeGraph g;
-            memset(&g.key, 0, sizeof(g.key));
             g.key = key;
             c->graphs.push_back(g);          // first sighting: run it live below
             hit = nullptr;

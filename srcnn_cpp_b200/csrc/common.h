@@ -92,8 +92,14 @@ struct PipeKey {
     float scale;
     int R0, R1;
     size_t dst_stride, dst_frame_stride;
-    int variant, fuse, host_bands, ka_kernel, ka_rows, seg_ovh;
+    int variant, fuse, host_bands, seg_ovh;
     void* stream;
+    bool operator==(const PipeKey& o) const {   // field by field: the struct has padding
+        return src == o.src && dst == o.dst && n == o.n && w == o.w && h == o.h && src_stride == o.src_stride &&
+               src_frame_stride == o.src_frame_stride && order == o.order && scale == o.scale && R0 == o.R0 && R1 == o.R1 &&
+               dst_stride == o.dst_stride && dst_frame_stride == o.dst_frame_stride && variant == o.variant && fuse == o.fuse &&
+               host_bands == o.host_bands && seg_ovh == o.seg_ovh && stream == o.stream;
+    }
 };
 struct PipeGraph {
     PipeKey key;

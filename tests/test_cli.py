@@ -111,3 +111,80 @@ def test_devices_option_splits_the_image_into_bands(tmp_path):
     assert d.max() <= 2 and (d <= 1).mean() >= 0.999
     r = _run("--devices=0,99", "--noverbose", src, many)      # a device that does not exist
     assert r.returncode != 0
+
+
+def _png(w, h, depth, ctype, rows, palette=None):
+    """Hand-made PNG (filter 0 on every row): rows = list of packed scanlines."""
+    import struct
+    import zlib
+
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xFFFFFFFF)
+    raw = b"".join(b"\x00" + bytes(r) for r in rows)
+    out = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, ctype, 0, 0, 0))
+    if palette is not None:
+        out += chunk(b"PLTE", bytes(palette))
+    return out + chunk(b"IDAT", zlib.compress(raw)) + chunk(b"IEND", b"")
+
+
+def _sub_byte_cases():
+    rng = np.random.default_rng(21)
+    w, h = 37, 23                                     # not a multiple of 8, 4 or 2 pixels per byte
+    cases = []
+    for depth in (1, 2, 4):
+        vals = rng.integers(0, 1 << depth, (h, w), dtype=np.uint8)
+        per = 8 // depth
+        rows = []
+        for y in range(h):
+            row = bytearray((w + per - 1) // per)
+            for x in range(w):
+                row[x // per] |= int(vals[y, x]) << ((per - 1 - x % per) * depth)
+            rows.append(row)
+        grey = (vals.astype(np.int32) * (255 // ((1 << depth) - 1))).astype(np.uint8)
+        cases.append(("grey%d" % depth, _png(w, h, depth, 0, rows), np.dstack([grey] * 3)))
+        pal = rng.integers(0, 256, (1 << depth, 3), dtype=np.uint8)          # R,G,B triples
+        cases.append(("pal%d" % depth, _png(w, h, depth, 3, rows, pal.reshape(-1)), pal[vals][:, :, ::-1]))   # -> BGR
+    return cases
+
+
+def test_png_sub_byte_depths_and_bad_headers_on_cpu(tmp_path):
+    """1/2/4-bit grey and palette PNGs decode (cv::imread accepts them, src/srcnn.cpp:462); a header with absurd dimensions
+    or a truncated stream is a load failure (exit -1), never a crash.  Without a GPU the run ends at context creation --
+    after the '- Image load' line, which is what this checks."""
+    import struct
+    for name, data, _ in _sub_byte_cases():
+        f = tmp_path / (name + ".png")
+        f.write_bytes(data)
+        r = _run(str(f), str(tmp_path / "o.png"))
+        assert "- Image load : " in r.stdout and "load failure" not in r.stdout, (name, r.stdout)
+    good = _sub_byte_cases()[0][1]
+    huge = bytearray(good)
+    huge[16:24] = struct.pack(">II", 0x7FFFFFFF, 0x7FFFFFFF)       # IHDR width / height (CRC is not checked by the reader)
+    for name, data in (("huge", bytes(huge)), ("cut", good[:len(good) - 30]), ("junk", b"\x89PNG\r\n\x1a\n" + b"\x00" * 40)):
+        f = tmp_path / (name + ".png")
+        f.write_bytes(data)
+        r = _run(str(f), str(tmp_path / "o.png"))
+        assert r.returncode == 255 and "- load failure :" in r.stdout, (name, r.returncode, r.stdout)
+
+
+def test_scale_values_that_are_ignored(tmp_path):
+    """--scale=0, a negative or an unparsable ratio leave the default 2.0 in place (src/srcnn.cpp:359-370)."""
+    for arg in ("--scale=0", "--scale=-3", "--scale=abc", "--scale="):
+        r = _run(arg, str(tmp_path / "nope.png"))
+        assert "- Scale multiply ratio : 2.00" in r.stdout and r.returncode == 255
+    r = _run("--scale=1.5", "--devices=0,1,x,,3", str(tmp_path / "nope.png"))
+    assert "- Scale multiply ratio : 1.50" in r.stdout and r.returncode == 255
+
+
+@pytest.mark.gpu
+def test_png_sub_byte_depths_decode_like_opencv(tmp_path, oracle):
+    """The decoded pixels are the ones cv::imread would hand the pipeline: FP32 variant == oracle on the expected BGR image."""
+    import cv2
+    for name, data, bgr in _sub_byte_cases():
+        f = tmp_path / (name + ".png")
+        f.write_bytes(data)
+        assert np.array_equal(cv2.imread(str(f)), bgr), name                 # the test's expectation is OpenCV's decode
+        out = str(tmp_path / (name + "_out.png"))
+        r = _run("--variant=fp32", "--noverbose", str(f), out)
+        assert r.returncode == 0, (name, r.stdout)
+        assert np.array_equal(cv2.imread(out), oracle.pipeline(np.ascontiguousarray(bgr), 2.0)), name
