@@ -225,6 +225,10 @@ __global__ void __launch_bounds__(256, 5) k_color_bicubic_tiled(ResizeDev p) {  
     // horizontal sums kept as float: they are integers below 2^24, so the conversion is exact and is done
     // once per sum instead of once per use in the vertical pass
     __shared__ __align__(16) float sH[3][kMaxSR][kTW];
+    // per tile row: the four vertical taps as floats (b_k = coef_k * 2^-22, exact) and the first tap's row in sH -- computed once
+    // per tile instead of once per (thread, row) in the vertical pass
+    __shared__ __align__(16) float4 sB[kTH];
+    __shared__ int sSr[kTH];
 
     const size_t fz = blockIdx.z;                       // frame of a batch
     const uint8_t* const fsrc = p.src + fz * p.src_frame;
@@ -237,17 +241,26 @@ __global__ void __launch_bounds__(256, 5) k_color_bicubic_tiled(ResizeDev p) {  
     const int nsc = sx_hi - sx_lo + 1, nsr = sy_hi - sy_lo + 1;
     const int tid = threadIdx.x;
 
-    // (1) colour-convert the footprint (replicate border applied here); i / nsc by multiply-shift (exact for i < 2^12)
+    if (tid < kTH && dy0 + tid < dy1) {
+        const short4 cy = p.ycoef[dy0 + tid];
+        const float sc = 1.0f / 4194304.0f;  // 2^-22, exact
+        sB[tid] = make_float4(__fmul_rn((float)cy.x, sc), __fmul_rn((float)cy.y, sc), __fmul_rn((float)cy.z, sc), __fmul_rn((float)cy.w, sc));
+        sSr[tid] = p.yofs[dy0 + tid] - 1 - sy_lo;
+    }
+    // (1) colour-convert the footprint (replicate border applied here); i / nsc by multiply-shift (exact for i < 2^12).
+    //     The B and R bytes are picked by pointer offset, the chroma clamps are one saturating conversion each.
     const unsigned rcp20 = ((1u << 20) + (unsigned)nsc - 1u) / (unsigned)nsc;
+    const int oB = p.swapRB ? 2 : 0, oR = 2 - oB;
     for (int i = tid; i < nsr * nsc; i += 256) {
         const int r = (int)(((unsigned)i * rcp20) >> 20), c = i - r * nsc;
         const int gy = clampi(sy_lo + r, 0, p.sh - 1) - p.src_row0;
         const int gx = clampi(sx_lo + c, 0, p.sw - 1);
         const uint8_t* px = fsrc + (size_t)gy * p.src_stride + 3 * (size_t)gx;
-        int c0 = px[0], c1 = px[1], c2 = px[2];
-        int B = p.swapRB ? c2 : c0, R = p.swapRB ? c0 : c2;
-        int Y, Cr, Cb;
-        bgr_to_ycc(B, c1, R, Y, Cr, Cb);
+        const int B = px[oB], G = px[1], R = px[oR];
+        const int Y = (1868 * B + 9617 * G + 4899 * R + 8192) >> 14;          // OpenCV RGB2YCrCb_i<uchar>, yuv_shift 14
+        uint32_t Cr, Cb;
+        asm("cvt.sat.u8.s32 %0, %1;" : "=r"(Cr) : "r"(((R - Y) * 11682 + (128 << 14) + 8192) >> 14));
+        asm("cvt.sat.u8.s32 %0, %1;" : "=r"(Cb) : "r"(((B - Y) * 9241 + (128 << 14) + 8192) >> 14));
         sP[0][r][c] = (uint8_t)Y;
         sP[1][r][c] = (uint8_t)Cr;
         sP[2][r][c] = (uint8_t)Cb;
@@ -319,11 +332,9 @@ __global__ void __launch_bounds__(256, 5) k_color_bicubic_tiled(ResizeDev p) {  
             for (int ty = tid >> 4; ty < kTH; ty += 16) {
                 const int dy = dy0 + ty;
                 if (dy >= dy1) break;
-                const int sr = p.yofs[dy] - 1 - sy_lo;
-                const short4 cy = p.ycoef[dy];
-                const float sc = 1.0f / 4194304.0f;  // 2^-22, exact
-                const float b0 = __fmul_rn((float)cy.x, sc), b1 = __fmul_rn((float)cy.y, sc);
-                const float b2 = __fmul_rn((float)cy.z, sc), b3 = __fmul_rn((float)cy.w, sc);
+                const int sr = sSr[ty];
+                const float4 bq = sB[ty];
+                const float b0 = bq.x, b1 = bq.y, b2 = bq.z, b3 = bq.w;
                 const size_t o = fplane + (size_t)(dy - p.plane_row0) * p.pitch + dx;
                 const unsigned long long bb0 = f2_pack(b0, b0), bb1 = f2_pack(b1, b1), bb2 = f2_pack(b2, b2), bb3 = f2_pack(b3, b3);
 #pragma unroll
@@ -376,7 +387,7 @@ __global__ void __launch_bounds__(256, 5) k_color_bicubic_tiled(ResizeDev p) {  
                         const float hh[4][4] = {{h0.x, h0.y, h0.z, h0.w}, {h1.x, h1.y, h1.z, h1.w}, {h2.x, h2.y, h2.z, h2.w}, {h3.x, h3.y, h3.z, h3.w}};
                         for (int j = 0; j < 4 && dx + j < dx1; j++) {
                             const int r = vertical_tap(__float2int_rn(hh[0][j]), __float2int_rn(hh[1][j]), __float2int_rn(hh[2][j]),
-                                                       __float2int_rn(hh[3][j]), cy, (dx + j) < p.simd_w);
+                                                       __float2int_rn(hh[3][j]), p.ycoef[dy], (dx + j) < p.simd_w);
                             if (pl == 0 && p.y16) {
                                 const unsigned short e = __half_as_ushort(__ushort2half_rn((unsigned short)r));
                                 unsigned short* q16 = reinterpret_cast<unsigned short*>(p.y16 + fy16 + (size_t)(dy - p.plane_row0) * p.pitch16) + kY16Pad + dx + j;
