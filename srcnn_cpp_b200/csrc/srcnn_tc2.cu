@@ -774,7 +774,7 @@ template <bool DBG, bool FUSED>
 __global__ void __launch_bounds__(kThreads, 1) k_srcnn_tc2(const Params p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x;
-    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform (see srcnn_tc.cu)
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform: a shuffled value, so ptxas keeps the role branches and the MMA issue paths uniform
     const int wg = warp >> 2;
     // the warp scheduler prefers the highest warp id: the role with the longest serial chain per row gets the highest
     // warpgroups.  wg 0,1: E2 (3)   wg 2,3: E1 (0)   wg 4,5: E3 (2)   wg 6,7: producer + conv1 issue (1)
