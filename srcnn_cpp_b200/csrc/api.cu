@@ -448,14 +448,14 @@ int host_pipeline(Ctx* c, const uint8_t* src, int n, int w, int h, size_t src_st
             const int nb = (int)std::min<long long>(by_mem, rows / 64);
             for (int bi = 1; bi < nb; bi++) edges.push_back(R0 + (int)((long long)rows * bi / nb));
         } else if (c->host_bands > 1) {
-            double len = std::max(256.0, (double)rows / c->host_bands);
+            double len = c->band_first > 0 ? (double)c->band_first : std::max(256.0, (double)rows / c->host_bands);
             int pos = R0;
             while ((int)edges.size() < c->host_bands) {
                 const int take = (int)len;
                 if (R1 - (pos + take) < take / 2) break;      // the rest joins the last band
                 pos += take;
                 edges.push_back(pos);
-                len *= 1.45;
+                len *= c->band_growth;
             }
         }
     }
@@ -477,7 +477,7 @@ int host_pipeline(Ctx* c, const uint8_t* src, int n, int w, int h, size_t src_st
     const bool graphable = c->use_graphs && !c->profiling && chunk >= n && bands * n <= 256;
     if (graphable) {
         PipeKey key{src, dst, n, w, h, src_stride, src_frame_stride, order, scale, R0, R1, dst_stride, dst_frame_stride, c->variant,
-                    (int)c->fuse_merge, c->host_bands, c->tc2_seg_ovh, (void*)c->stream};
+                    (int)c->fuse_merge, c->host_bands * 4096 + c->band_first, c->tc2_seg_ovh + (int)(c->band_growth * 1000.0) * 256, (void*)c->stream};
         for (auto& g : c->graphs)
             if (g.key == key) hit = &g;
         if (!hit) {
@@ -617,6 +617,8 @@ int srcnn_create(srcnn_ctx** out, int device, int variant) {
     if (const char* k = getenv("SRCNN_TC2_SEG_OVH")) c->tc2_seg_ovh = std::max(0, std::min(64, atoi(k)));   // tuning aid
     if (const char* k = getenv("SRCNN_BATCH_LAUNCH")) c->batch_launch = atoi(k) != 0;                        // A/B aid
     if (const char* k = getenv("SRCNN_GRAPHS")) c->use_graphs = atoi(k) != 0;                                // A/B aid
+    if (const char* k = getenv("SRCNN_BAND_FIRST")) c->band_first = std::max(0, atoi(k));                       // tuning aids: rows of the first
+    if (const char* k = getenv("SRCNN_BAND_GROWTH")) c->band_growth = std::max(1.0, std::min(4.0, atof(k)));   // sub-band, growth per band
     if (const char* k = getenv("SRCNN_HOST_BANDS")) c->host_bands = std::max(1, std::min(64, atoi(k)));     // tuning aid
     *out = c;
     return SRCNN_OK;
@@ -679,6 +681,13 @@ extern "C" __attribute__((visibility("default"))) int srcnn_debug_set_tc2_seg_ov
 extern "C" __attribute__((visibility("default"))) int srcnn_debug_set_host_bands(srcnn_ctx* c, int bands) {
     if (!c || bands < 1 || bands > 64) return SRCNN_E_ARG;
     c->host_bands = bands;
+    return SRCNN_OK;
+}
+// tuning hook: rows of the first sub-band of a single host frame (0 = rows / host_bands, at least 256) and the growth per band
+extern "C" __attribute__((visibility("default"))) int srcnn_debug_set_band_schedule(srcnn_ctx* c, int first_rows, double growth) {
+    if (!c || first_rows < 0 || !(growth >= 1.0 && growth <= 4.0)) return SRCNN_E_ARG;
+    c->band_first = first_rows;
+    c->band_growth = growth;
     return SRCNN_OK;
 }
 // test hook: a device-resident batch as one launch per stage and chunk (default) or frame by frame

@@ -127,6 +127,8 @@ struct Ctx {
                                      // (SRCNN_FUSE_MERGE=1; byte-identical, but 0.236 vs 0.214 ms per 4K frame: off by default)
     Tc2Partition tc2_part;
     bool batch_launch = true;        // device-resident batches: one launch per stage and chunk of frames (SRCNN_BATCH_LAUNCH=0: frame by frame)
+    int band_first = 0;              // host-buffer pipeline: rows of a single frame's first sub-band (0 = rows / host_bands, >= 256) ...
+    double band_growth = 1.3;        // ... and how much longer each following sub-band is (tools/e2e_sweep.py: flat optimum 1.3-1.5)
     int host_bands = 8;              // host-buffer pipeline: most sub-bands a single frame is cut into (SRCNN_HOST_BANDS)
     int tc2_seg_ovh = 12;            // cost of opening a segment, in row steps (SRCNN_TC2_SEG_OVH; 0 = cut into equal row counts)
     int* d_guard = nullptr;          // device-side watchdog flag (mapped pinned)
