@@ -10,12 +10,12 @@ CSRC := srcnn_cpp_b200/csrc
 OBJ := build/obj
 LIB := srcnn_cpp_b200/libsrcnn_b200.so
 WEIGHTS := $(abspath srcnn_cpp_b200/data/srcnn_weights.bin)
-CU := api mgpu jpeg_stream color_bicubic srcnn_fp32 srcnn_tc2 fraw_resize
+CU := api mgpu jpeg_stream color_bicubic color_bicubic_int srcnn_fp32 srcnn_tc2 fraw_resize
 OBJS := $(addprefix $(OBJ)/,$(addsuffix .o,$(CU))) $(OBJ)/weights_blob.o $(OBJ)/libsrcnn.o
 
 all: $(LIB) bin/srcnn oracle
 
-$(OBJ)/%.o: $(CSRC)/%.cu $(CSRC)/common.h $(CSRC)/weights.h include/srcnn_b200.h
+$(OBJ)/%.o: $(CSRC)/%.cu $(CSRC)/common.h $(CSRC)/color_bicubic.h $(CSRC)/weights.h include/srcnn_b200.h
 	@mkdir -p $(OBJ)
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(OBJ)/$*.ptxas.log || (cat $(OBJ)/$*.ptxas.log; false)
 	@grep -E "error|warning|spill|registers" $(OBJ)/$*.ptxas.log | grep -v "0 bytes spill" | head -40 || true
