@@ -618,7 +618,6 @@ int srcnn_create(srcnn_ctx** out, int device, int variant) {
     if (const char* k = getenv("SRCNN_BATCH_LAUNCH")) c->batch_launch = atoi(k) != 0;                        // A/B aid
     if (const char* k = getenv("SRCNN_KA_INT")) c->ka_int = atoi(k) != 0;                                    // A/B aid
     if (const char* k = getenv("SRCNN_KA_ISR")) c->ka_int_isr = atoi(k);                                     // A/B aid
-    if (const char* k = getenv("SRCNN_KA_TMA")) c->ka_int_tma = atoi(k) != 0;                                // A/B aid
     if (const char* k = getenv("SRCNN_GRAPHS")) c->use_graphs = atoi(k) != 0;                                // A/B aid
     if (const char* k = getenv("SRCNN_BAND_FIRST")) c->band_first = std::max(0, atoi(k));                       // tuning aids: rows of the first
     if (const char* k = getenv("SRCNN_BAND_GROWTH")) c->band_growth = std::max(1.0, std::min(4.0, atof(k)));   // sub-band, growth per band

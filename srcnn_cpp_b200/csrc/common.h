@@ -131,7 +131,6 @@ struct Ctx {
     int band_first = 0;              // host-buffer pipeline: rows of a single frame's first sub-band (0 = rows / host_bands, >= 256) ...
     double band_growth = 1.3;        // ... and how much longer each following sub-band is (tools/e2e_sweep.py: flat optimum 1.3-1.5)
     int host_bands = 8;              // host-buffer pipeline: most sub-bands a single frame is cut into (SRCNN_HOST_BANDS)
-    bool ka_int_tma = true;          // ... with a tile's source rows fetched by TMA (SRCNN_KA_TMA=0: per-thread loads)
     int ka_int_isr = 0;              // ... tile height in source rows, 0 = chosen per launch (SRCNN_KA_ISR, A/B aid)
     bool ka_int = true;              // colour+bicubic: the integer-scale kernel for x2 / x4 (SRCNN_KA_INT=0: always the generic tiled kernel)
     int tc2_seg_ovh = 12;            // cost of opening a segment, in row steps (SRCNN_TC2_SEG_OVH; 0 = cut into equal row counts)
