@@ -222,10 +222,13 @@ class Engine:
         self._check(self.L.srcnn_sync(self.ctx))
 
     def profile_enable(self, on=True):
-        self._check(self.L.srcnn_profile_enable(self.ctx, 1 if on else 0))
+        """on: False / True (events around all three stages: the stages then run strictly one after another) / 2 (events around
+        the CNN stage only: the merge of one call and the colour+bicubic of the next stay adjacent and may overlap)"""
+        self._check(self.L.srcnn_profile_enable(self.ctx, 2 if on == 2 else (1 if on else 0)))
 
     def profile_read(self):
-        """-> ([ms colour+bicubic, ms fused SRCNN, ms merge], number of whole-path calls)"""
+        """-> ([ms colour+bicubic, ms fused SRCNN, ms merge], number of whole-path calls); in mode 2: [ms between consecutive CNN
+        launches (merge of call i beside colour+bicubic of call i+1), ms fused SRCNN, 0]"""
         ms = (C.c_double * 3)()
         n = C.c_int()
         self._check(self.L.srcnn_profile_read(self.ctx, ms, C.byref(n)))

@@ -43,8 +43,12 @@ int ensure(Ctx* c, DevBuf& b, size_t bytes) {
     return SRCNN_OK;
 }
 
-int prof_mark(Ctx* c) {
+// `which`: 0 before colour+bicubic, 1 after it, 2 after the CNN stage, 3 after the merge.  Mode 2 keeps only the pair around
+// the CNN stage: an event between the merge of one call and the colour+bicubic of the next would separate the two kernels
+// in the stream and switch their overlap off.
+int prof_mark(Ctx* c, int which) {
     if (!c->profiling) return SRCNN_OK;
+    if (c->profiling == 2 && which != 1 && which != 2) return SRCNN_OK;
     if (c->ev_used == c->ev_pool.size()) {
         cudaEvent_t e;
         SRCNN_CUDA(c, cudaEventCreate(&e));
@@ -76,15 +80,22 @@ static int check_image(Ctx* c, const void* src, int w, int h, size_t stride, int
 }
 
 // planes of `nframes` same-sized frames: [Y frames][Cr frames][Cb frames][Y' frames][FP16 Y frames]
+// Cross-call overlap: device-resident whole-path calls alternate between two plane sets (when a set is at most 8 GiB), so
+// that nothing the colour+bicubic kernel of call i+1 writes is read by the merge kernel of call i; c->plane_sel says which
+// set this call got.  The host-buffer pipeline keeps to set 0 (its sub-bands are separated by copies and events anyway).
 static int carve_planes(Ctx* c, int ow, int rows, int row0, Planes* pl, int nframes = 1) {
     const size_t pitch = align_up((size_t)ow, 128);
     const size_t plane = pitch * (size_t)rows;
     const size_t pitch16 = y16_pitch_bytes(ow);
     const size_t plane16 = align_up(pitch16 * (size_t)rows, 256);
     const size_t nf = (size_t)nframes;
-    int rc = ensure(c, c->plane_buf, (plane * 4 + plane16) * nf + 512);   // slack: the last row's last strip copy may run past the row
+    const size_t bytes = (plane * 4 + plane16) * nf + 512;   // slack: the last row's last strip copy may run past the row
+    const bool two = c->overlap && !c->host_path && !c->capturing && bytes <= ((size_t)8 << 30);
+    c->plane_sel = two ? (c->plane_sel ^ 1) : 0;
+    DevBuf& buf = c->plane_sel ? c->plane_buf2 : c->plane_buf;
+    int rc = ensure(c, buf, bytes);
     if (rc) return rc;
-    uint8_t* base = (uint8_t*)c->plane_buf.p;
+    uint8_t* base = (uint8_t*)buf.p;
     pl->y = base;
     pl->cr = base + plane * nf;
     pl->cb = base + 2 * plane * nf;
@@ -97,6 +108,22 @@ static int carve_planes(Ctx* c, int ow, int rows, int row0, Planes* pl, int nfra
     pl->row0 = row0;
     pl->rows = rows;
     return SRCNN_OK;
+}
+
+// May the colour+bicubic kernel about to be enqueued start while the stream's previous kernel is still running?  Only when that
+// kernel is a merge of ours (launch_merge lets its dependents go at once) which reads the OTHER plane set and writes nothing
+// this call's source overlaps (a caller may feed one call's result to the next).  Anything the caller put on the stream in
+// between simply keeps the usual order: the early start is a property of two adjacent kernels (programmatic dependent launch).
+static bool may_start_early(Ctx* c, const uint8_t* src, size_t src_bytes) {
+    if (!c->overlap || c->host_path || c->capturing || c->profiling == 1) return false;
+    if (c->merge_sel < 0 || c->merge_sel == c->plane_sel || c->merge_stream != c->stream) return false;
+    return src + src_bytes <= c->merge_lo || src >= c->merge_hi;
+}
+static void merged_into(Ctx* c, const uint8_t* dst, size_t bytes) {   // after the whole-path call's (last) launch_merge
+    c->merge_sel = c->plane_sel;
+    c->merge_stream = c->stream;
+    c->merge_lo = dst;
+    c->merge_hi = dst + bytes;
 }
 
 static int run_cnn(Ctx* c, int variant, const CnnArgs& a) {
@@ -134,10 +161,12 @@ static int process_rows_impl(Ctx* c, const uint8_t* d_src, int w, int h, size_t 
     ra.row_begin = p0; ra.row_end = p1;
     ra.pl = pl; ra.tx = tx; ra.ty = ty;
     if (c->variant != SRCNN_VARIANT_TC) ra.pl.y16 = nullptr;      // the strict FP32 kernels read the u8 plane
-    if ((rc = prof_mark(c))) return rc;
+    ra.early = may_start_early(c, d_src, (size_t)(s1 - s0) * src_stride);
+    c->early_launches += ra.early;
+    if ((rc = prof_mark(c, 0))) return rc;
     rc = launch_color_bicubic(c, ra);
     if (rc) return rc;
-    if ((rc = prof_mark(c))) return rc;
+    if ((rc = prof_mark(c, 1))) return rc;
 
     c->fail_stage = SRCNN_STAGE_CNN;
     CnnArgs ca;
@@ -156,8 +185,8 @@ static int process_rows_impl(Ctx* c, const uint8_t* d_src, int w, int h, size_t 
     }
     rc = run_cnn(c, c->variant, ca);
     if (rc) return rc;
-    if ((rc = prof_mark(c))) return rc;
-    if (fused) return prof_mark(c);
+    if ((rc = prof_mark(c, 2))) return rc;
+    if (fused) return prof_mark(c, 3);
 
     c->fail_stage = SRCNN_STAGE_MERGE;
     MergeArgs ma;
@@ -168,7 +197,8 @@ static int process_rows_impl(Ctx* c, const uint8_t* d_src, int w, int h, size_t 
     ma.dst = d_dst; ma.dst_stride = dst_stride;
     rc = launch_merge(c, ma);
     if (rc) return rc;
-    return prof_mark(c);
+    merged_into(c, d_dst, (size_t)(r1 - r0) * dst_stride);
+    return prof_mark(c, 3);
 }
 
 static int process_rows(Ctx* c, const uint8_t* d_src, int w, int h, size_t src_stride, int s0, int s1, int order,
@@ -206,9 +236,11 @@ static int process_frames_impl(Ctx* c, const uint8_t* d_src, int n, int w, int h
         ra.row_begin = 0; ra.row_end = oh;
         ra.pl = pl; ra.tx = tx; ra.ty = ty;
         ra.nframes = m; ra.src_frame_stride = src_frame_stride;
-        if ((rc = prof_mark(c))) return rc;
+        ra.early = may_start_early(c, ra.src, (size_t)(m - 1) * src_frame_stride + (size_t)h * src_stride);
+        c->early_launches += ra.early;
+        if ((rc = prof_mark(c, 0))) return rc;
         if ((rc = launch_color_bicubic(c, ra))) return rc;
-        if ((rc = prof_mark(c))) return rc;
+        if ((rc = prof_mark(c, 1))) return rc;
         c->fail_stage = SRCNN_STAGE_CNN;
         CnnArgs ca;
         ca.y = pl.y; ca.pitch = pl.pitch;
@@ -219,7 +251,7 @@ static int process_frames_impl(Ctx* c, const uint8_t* d_src, int n, int w, int h
         ca.out = pl.yout; ca.out_pitch = pl.pitch;
         ca.nframes = m; ca.y16_frame_stride = pl.frame_stride16; ca.out_frame_stride = pl.frame_stride;
         if ((rc = launch_cnn_tc2(c, ca))) return rc;
-        if ((rc = prof_mark(c))) return rc;
+        if ((rc = prof_mark(c, 2))) return rc;
         c->fail_stage = SRCNN_STAGE_MERGE;
         MergeArgs ma;
         ma.y = pl.yout; ma.cr = pl.cr; ma.cb = pl.cb;
@@ -236,7 +268,8 @@ static int process_frames_impl(Ctx* c, const uint8_t* d_src, int n, int w, int h
                 if ((rc = launch_merge(c, ma))) return rc;
             }
         }
-        if ((rc = prof_mark(c))) return rc;
+        merged_into(c, dst0, (size_t)(m - 1) * dst_frame_stride + (size_t)oh * dst_stride);
+        if ((rc = prof_mark(c, 3))) return rc;
     }
     return SRCNN_OK;
 }
@@ -414,6 +447,11 @@ static int enqueue_chunk(Ctx* c, const uint8_t* src, int f0, int m, int w, int h
 int host_pipeline(Ctx* c, const uint8_t* src, int n, int w, int h, size_t src_stride, size_t src_frame_stride, int order,
                   float scale, int ow, int oh, int R0, int R1, uint8_t* dst, size_t dst_stride, size_t dst_frame_stride) {
     int rc;
+    struct HostPath {   // the pipeline's sub-bands and groups share plane set 0 (carve_planes) and never start early
+        Ctx* c;
+        explicit HostPath(Ctx* c_) : c(c_) { c->host_path = true; c->merge_sel = -1; }
+        ~HostPath() { c->host_path = false; c->merge_sel = -1; }
+    } host_path{c};
     TapTable *ty = nullptr, *tx = nullptr;
     if ((rc = get_taps(c, h, oh, &ty))) return rc;
     if ((rc = get_taps(c, w, ow, &tx))) return rc;      // uploaded here, not inside a graph capture
@@ -619,6 +657,8 @@ int srcnn_create(srcnn_ctx** out, int device, int variant) {
     if (const char* k = getenv("SRCNN_KA_INT")) c->ka_int = atoi(k) != 0;                                    // A/B aid
     if (const char* k = getenv("SRCNN_KA_ISR")) c->ka_int_isr = atoi(k);                                     // A/B aid
     if (const char* k = getenv("SRCNN_GRAPHS")) c->use_graphs = atoi(k) != 0;                                // A/B aid
+    if (const char* k = getenv("SRCNN_OVERLAP")) c->overlap = atoi(k) != 0;                                  // A/B aid
+    if (const char* k = getenv("SRCNN_MERGE_CTAS")) c->merge_ctas_per_sm = std::max(1, std::min(8, atoi(k))); // tuning aid
     if (const char* k = getenv("SRCNN_BAND_FIRST")) c->band_first = std::max(0, atoi(k));                       // tuning aids: rows of the first
     if (const char* k = getenv("SRCNN_BAND_GROWTH")) c->band_growth = std::max(1.0, std::min(4.0, atof(k)));   // sub-band, growth per band
     if (const char* k = getenv("SRCNN_HOST_BANDS")) c->host_bands = std::max(1, std::min(64, atoi(k)));     // tuning aid
@@ -637,7 +677,7 @@ int srcnn_destroy(srcnn_ctx* c) {
         if (t.d_ofs) cudaFree(t.d_ofs);
         if (t.d_coef) cudaFree(t.d_coef);
     }
-    for (DevBuf* b : {&c->plane_buf, &c->y16_buf, &c->act2_buf, &c->src_buf, &c->dst_buf, &c->work_buf})
+    for (DevBuf* b : {&c->plane_buf, &c->plane_buf2, &c->y16_buf, &c->act2_buf, &c->src_buf, &c->dst_buf, &c->work_buf})
         if (b->p) cudaFree(b->p);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     for (cudaEvent_t e : c->pipe_events) cudaEventDestroy(e);
@@ -698,6 +738,13 @@ extern "C" __attribute__((visibility("default"))) int srcnn_debug_set_batch_laun
     c->batch_launch = on != 0;
     return SRCNN_OK;
 }
+// test hook: cross-call overlap (two plane sets; colour+bicubic of call i+1 beside the merge of call i) on / off; returns
+// how many colour+bicubic launches so far were allowed to start early
+extern "C" __attribute__((visibility("default"))) long long srcnn_debug_overlap(srcnn_ctx* c, int on) {
+    if (!c) return SRCNN_E_ARG;
+    if (on >= 0) { c->overlap = on != 0; c->merge_sel = -1; }
+    return c->early_launches;
+}
 // test hook: CUDA-graph replay of repeated host-buffer calls on / off; returns the number of instantiated graphs
 extern "C" __attribute__((visibility("default"))) int srcnn_debug_graphs(srcnn_ctx* c, int on) {
     if (!c) return SRCNN_E_ARG;
@@ -729,7 +776,7 @@ int srcnn_device_sm_count(srcnn_ctx* c) { return c ? c->sm_count : SRCNN_E_ARG; 
 int srcnn_profile_enable(srcnn_ctx* c, int on) {
     ENTER(c);
     SRCNN_CUDA(c, cudaStreamSynchronize(c->stream));
-    c->profiling = on != 0;
+    c->profiling = on == 2 ? 2 : (on != 0);
     c->ev_used = 0;
     c->prof_calls = 0;
     return SRCNN_OK;
@@ -737,18 +784,33 @@ int srcnn_profile_enable(srcnn_ctx* c, int on) {
 
 // Sums the device time of the three stages over every band processed since the last read:
 // ms[0] colour+bicubic, ms[1] fused SRCNN, ms[2] merge+colour-back; *calls = number of whole-path API calls.
+// Mode 2 (events around the CNN stage only): ms[1] as above; ms[0] = the time BETWEEN consecutive CNN launches, i.e. the merge
+// of one call and the colour+bicubic of the next running side by side (n - 1 intervals for n launches); ms[2] = 0.
 int srcnn_profile_read(srcnn_ctx* c, double* ms, int* calls) {
     ENTER(c);
     if (!ms || !calls) return fail(c, SRCNN_E_ARG, "null pointer");
     SRCNN_CUDA(c, cudaStreamSynchronize(c->stream));
     ms[0] = ms[1] = ms[2] = 0.0;
-    const size_t n = c->ev_used / 4;
-    for (size_t i = 0; i < n; i++)
-        for (int k = 0; k < 3; k++) {
+    if (c->profiling == 2) {
+        const size_t n = c->ev_used / 2;
+        for (size_t i = 0; i < n; i++) {
             float t = 0.f;
-            SRCNN_CUDA(c, cudaEventElapsedTime(&t, c->ev_pool[4 * i + k], c->ev_pool[4 * i + k + 1]));
-            ms[k] += t;
+            SRCNN_CUDA(c, cudaEventElapsedTime(&t, c->ev_pool[2 * i], c->ev_pool[2 * i + 1]));
+            ms[1] += t;
+            if (i + 1 < n) {
+                SRCNN_CUDA(c, cudaEventElapsedTime(&t, c->ev_pool[2 * i + 1], c->ev_pool[2 * i + 2]));
+                ms[0] += t;
+            }
         }
+    } else {
+        const size_t n = c->ev_used / 4;
+        for (size_t i = 0; i < n; i++)
+            for (int k = 0; k < 3; k++) {
+                float t = 0.f;
+                SRCNN_CUDA(c, cudaEventElapsedTime(&t, c->ev_pool[4 * i + k], c->ev_pool[4 * i + k + 1]));
+                ms[k] += t;
+            }
+    }
     *calls = c->prof_calls;
     c->ev_used = 0;
     c->prof_calls = 0;

@@ -559,56 +559,82 @@ __device__ __forceinline__ uint32_t pack_sat_u8(int lo, int hi, uint32_t upper) 
     return d;
 }
 
+// A grid of at most a few CTAs per SM walks the 16-pixel groups of the image (row-major, grid-stride): every CTA is resident from
+// the start, so the kernel can let its dependents go at once (griddepcontrol.launch_dependents) -- the colour+bicubic kernel of
+// the NEXT whole-path call, when api.cu launched it with programmatic stream serialisation, then fills the SMs' free warp slots
+// while this kernel, which is bound by L2 / HBM and leaves the issue slots idle, is still running.  A kernel launched the
+// ordinary way waits for this one to finish as always.
 __global__ void __launch_bounds__(256) k_merge_ycc2bgr_v16(const uint8_t* __restrict__ y, const uint8_t* __restrict__ cr,
                                                            const uint8_t* __restrict__ cb, size_t pitch, int w, int rows,
                                                            int swapRB, uint8_t* __restrict__ dst, size_t dst_stride,
-                                                           int blocks_per_row) {
-    const int row = blockIdx.x / blocks_per_row;
-    const int g = (blockIdx.x - row * blocks_per_row) * blockDim.x + threadIdx.x;  // 16-pixel group
-    const int x = g * 16;
-    if (x >= w || row >= rows) return;
-    const size_t o = (size_t)row * pitch + x;
-    const uint4 vy = *reinterpret_cast<const uint4*>(y + o);
-    const uint4 vr = *reinterpret_cast<const uint4*>(cr + o);
-    const uint4 vb = *reinterpret_cast<const uint4*>(cb + o);
-    const uint32_t wy[4] = {vy.x, vy.y, vy.z, vy.w}, wr[4] = {vr.x, vr.y, vr.z, vr.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
+                                                           int groups_per_row) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     // 16-bit coefficient pairs (low half x Cb-128, high half x Cr-128): B = 29049 cb, G = -5636 cb - 11698 cr, R = 22987 cr
     const uint32_t kB = 29049u, kG = (uint32_t)(unsigned short)(-5636) | ((uint32_t)(unsigned short)(-11698) << 16), kR = 22987u << 16;
     const uint32_t k0 = swapRB ? kR : kB, k2 = swapRB ? kB : kR;      // first and third byte of a pixel
-    uint32_t outw[12];
-#pragma unroll
-    for (int k = 0; k < 4; k++) {   // 4 pixels -> 12 bytes -> 3 words
-        const uint32_t sb = wb[k] ^ 0x80808080u, sr = wr[k] ^ 0x80808080u;     // Cb-128, Cr-128 as signed bytes
-        const uint32_t c01 = __byte_perm(sb, sr, 0x5140), c23 = __byte_perm(sb, sr, 0x7362);   // (cb0,cr0,cb1,cr1), (cb2,cr2,cb3,cr3)
-        int v[4][3];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int t = (int)((wy[k] >> (8 * j)) & 255u) * 16384 + 8192;
-            const uint32_t cc = j < 2 ? c01 : c23;
-            if (j & 1) {
-                v[j][0] = dp2a_hi_ss(k0, cc, t) >> 14;
-                v[j][1] = dp2a_hi_ss(kG, cc, t) >> 14;
-                v[j][2] = dp2a_hi_ss(k2, cc, t) >> 14;
-            } else {
-                v[j][0] = dp2a_lo_ss(k0, cc, t) >> 14;
-                v[j][1] = dp2a_lo_ss(kG, cc, t) >> 14;
-                v[j][2] = dp2a_lo_ss(k2, cc, t) >> 14;
-            }
-        }
-        // bytes: p0c0 p0c1 p0c2 p1c0 | p1c1 p1c2 p2c0 p2c1 | p2c2 p3c0 p3c1 p3c2
-        outw[3 * k] = pack_sat_u8(v[0][0], v[0][1], pack_sat_u8(v[0][2], v[1][0], 0u));
-        outw[3 * k + 1] = pack_sat_u8(v[1][1], v[1][2], pack_sat_u8(v[2][0], v[2][1], 0u));
-        outw[3 * k + 2] = pack_sat_u8(v[2][2], v[3][0], pack_sat_u8(v[3][1], v[3][2], 0u));
+    // (row, group) of this thread's items without a division per item: one step of the grid-stride walk is `srow` rows and `sgrp`
+    // groups further, with a carry into the next row.  The next item's three 16-byte loads are in flight while this one is
+    // converted and stored.
+    const unsigned stride = gridDim.x * blockDim.x;
+    const unsigned first = blockIdx.x * blockDim.x + threadIdx.x;
+    const int srow = (int)(stride / (unsigned)groups_per_row), sgrp = (int)(stride % (unsigned)groups_per_row);
+    int row = (int)(first / (unsigned)groups_per_row), grp = (int)(first % (unsigned)groups_per_row);
+    if (row >= rows) return;
+    uint4 vy, vr, vb;
+    {
+        const size_t o = (size_t)row * pitch + grp * 16;
+        vy = *reinterpret_cast<const uint4*>(y + o);
+        vr = *reinterpret_cast<const uint4*>(cr + o);
+        vb = *reinterpret_cast<const uint4*>(cb + o);
     }
-    uint8_t* d = dst + (size_t)row * dst_stride + 3 * (size_t)x;
-    if (x + 15 < w) {
-        uint4* d4 = reinterpret_cast<uint4*>(d);
-        d4[0] = make_uint4(outw[0], outw[1], outw[2], outw[3]);
-        d4[1] = make_uint4(outw[4], outw[5], outw[6], outw[7]);
-        d4[2] = make_uint4(outw[8], outw[9], outw[10], outw[11]);
-    } else {
-        const int n = (w - x) * 3;
-        for (int j = 0; j < n; j++) d[j] = (uint8_t)(outw[j >> 2] >> (8 * (j & 3)));
+    for (;;) {
+        const int x = grp * 16, crow = row;
+        const uint32_t wy[4] = {vy.x, vy.y, vy.z, vy.w}, wr[4] = {vr.x, vr.y, vr.z, vr.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
+        row += srow; grp += sgrp;
+        if (grp >= groups_per_row) { grp -= groups_per_row; row++; }
+        const bool more = row < rows;
+        if (more) {
+            const size_t o = (size_t)row * pitch + grp * 16;
+            vy = *reinterpret_cast<const uint4*>(y + o);
+            vr = *reinterpret_cast<const uint4*>(cr + o);
+            vb = *reinterpret_cast<const uint4*>(cb + o);
+        }
+        uint32_t outw[12];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {   // 4 pixels -> 12 bytes -> 3 words
+            const uint32_t sb = wb[k] ^ 0x80808080u, sr = wr[k] ^ 0x80808080u;     // Cb-128, Cr-128 as signed bytes
+            const uint32_t c01 = __byte_perm(sb, sr, 0x5140), c23 = __byte_perm(sb, sr, 0x7362);   // (cb0,cr0,cb1,cr1), (cb2,cr2,cb3,cr3)
+            int v[4][3];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int t = (int)((wy[k] >> (8 * j)) & 255u) * 16384 + 8192;
+                const uint32_t cc = j < 2 ? c01 : c23;
+                if (j & 1) {
+                    v[j][0] = dp2a_hi_ss(k0, cc, t) >> 14;
+                    v[j][1] = dp2a_hi_ss(kG, cc, t) >> 14;
+                    v[j][2] = dp2a_hi_ss(k2, cc, t) >> 14;
+                } else {
+                    v[j][0] = dp2a_lo_ss(k0, cc, t) >> 14;
+                    v[j][1] = dp2a_lo_ss(kG, cc, t) >> 14;
+                    v[j][2] = dp2a_lo_ss(k2, cc, t) >> 14;
+                }
+            }
+            // bytes: p0c0 p0c1 p0c2 p1c0 | p1c1 p1c2 p2c0 p2c1 | p2c2 p3c0 p3c1 p3c2
+            outw[3 * k] = pack_sat_u8(v[0][0], v[0][1], pack_sat_u8(v[0][2], v[1][0], 0u));
+            outw[3 * k + 1] = pack_sat_u8(v[1][1], v[1][2], pack_sat_u8(v[2][0], v[2][1], 0u));
+            outw[3 * k + 2] = pack_sat_u8(v[2][2], v[3][0], pack_sat_u8(v[3][1], v[3][2], 0u));
+        }
+        uint8_t* d = dst + (size_t)crow * dst_stride + 3 * (size_t)x;
+        if (x + 15 < w) {
+            uint4* d4 = reinterpret_cast<uint4*>(d);
+            d4[0] = make_uint4(outw[0], outw[1], outw[2], outw[3]);
+            d4[1] = make_uint4(outw[4], outw[5], outw[6], outw[7]);
+            d4[2] = make_uint4(outw[8], outw[9], outw[10], outw[11]);
+        } else {
+            const int n = (w - x) * 3;
+            for (int j = 0; j < n; j++) d[j] = (uint8_t)(outw[j >> 2] >> (8 * (j & 3)));
+        }
+        if (!more) break;
     }
 }
 
@@ -616,11 +642,17 @@ int launch_merge(Ctx* c, const MergeArgs& a) {
     if (a.rows <= 0 || a.w <= 0) return SRCNN_OK;
     const bool wide = ((((uintptr_t)a.dst) | a.dst_stride | (uintptr_t)a.y | (uintptr_t)a.cr | (uintptr_t)a.cb | a.pitch) & 15) == 0 &&
                       a.pitch >= align_up((size_t)a.w, 16);
+    c->merge_sel = -1;   // a whole-path caller says afterwards which plane set this launch reads (api.cu, merged_into)
     if (wide) {
         const int groups16 = (a.w + 15) / 16;
-        const int bpr16 = (groups16 + 255) / 256;
-        k_merge_ycc2bgr_v16<<<(unsigned)bpr16 * (unsigned)a.rows, 256, 0, c->stream>>>(a.y, a.cr, a.cb, a.pitch, a.w, a.rows,
-                                                                                    a.order == SRCNN_ORDER_RGB, a.dst, a.dst_stride, bpr16);
+        const long long ngroups = (long long)groups16 * a.rows;
+        // every CTA resident at once (the kernel lets its dependents go on entry): kMergeCtasPerSm per SM at most
+        // ... and every thread gets the same number of groups (k), as far as the total allows
+        const long long want = (ngroups + 255) / 256, cap = (long long)c->merge_ctas_per_sm * std::max(1, c->sm_count);
+        const long long k = (want + cap - 1) / cap;
+        const int grid = (int)((want + k - 1) / k);
+        k_merge_ycc2bgr_v16<<<grid, 256, 0, c->stream>>>(a.y, a.cr, a.cb, a.pitch, a.w, a.rows, a.order == SRCNN_ORDER_RGB, a.dst,
+                                                        a.dst_stride, groups16);
         c->launches++;
         SRCNN_CUDA(c, cudaGetLastError());
         return SRCNN_OK;

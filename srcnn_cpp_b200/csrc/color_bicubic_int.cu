@@ -281,12 +281,17 @@ __global__ void __launch_bounds__(96, S == 2 ? SRCNN_KA_MINB : 6) k_color_bicubi
     __syncthreads();
     // (2) the walk
     walk_tile<S>(p, t, &sP[tid >> 5][0][0], tid >> 5, tid & 31, X0, a, nit, fz);
+    // Launched with programmatic stream serialisation (api.cu, may_start_early) this grid may have started while the merge kernel
+    // of the previous whole-path call was still running; nothing here depends on it.  The last tile waits for that kernel at its
+    // very end, so that "this grid has finished" still implies "everything before it in the stream has finished" for whatever
+    // follows.  A no-op after an ordinary launch.
+    if (tile == t.ntiles - 1) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 inline int floordiv(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
 
 template <int S>
-int launch_variant(Ctx* c, const ResizeDev& p, IntTaps& t, int nframes) {
+int launch_variant(Ctx* c, const ResizeDev& p, IntTaps& t, int nframes, bool early) {
     static int ctas_per_sm[64] = {0};              // per device; a benign race: every writer stores the same value
     int& per_sm = ctas_per_sm[c->device & 63];
     if (per_sm == 0) {
@@ -307,7 +312,21 @@ int launch_variant(Ctx* c, const ResizeDev& p, IntTaps& t, int nframes) {
     if (ntiles > 0x3fffffffLL) return SRCNN_E_ARG;
     t.nty = (nrows + t.isr - 1) / t.isr;
     t.ntiles = (int)ntiles;
-    k_color_bicubic_int<S><<<t.ntiles, 96, 0, c->stream>>>(p, t);
+    if (early) {   // programmatic dependent launch: may begin before the stream's previous kernel (a merge of ours) has finished
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)t.ntiles);
+        cfg.blockDim = dim3(96);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = c->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        SRCNN_CUDA(c, cudaLaunchKernelEx(&cfg, k_color_bicubic_int<S>, p, t));
+    } else {
+        k_color_bicubic_int<S><<<t.ntiles, 96, 0, c->stream>>>(p, t);
+    }
     c->launches++;
     SRCNN_CUDA(c, cudaGetLastError());
     return SRCNN_OK;
@@ -345,7 +364,7 @@ int launch_color_bicubic_int(Ctx* c, const ResizeDev& p, const ResizeArgs& a, bo
     const int nframes = std::max(1, a.nframes);
     t.ntx = (a.ow + kITW - 1) / kITW;
     if ((long long)t.ntx * (t.i_last - t.a_first + 1) * nframes > 0x3fffffffLL) return SRCNN_OK;
-    const int rc = S == 2 ? launch_variant<2>(c, p, t, nframes) : launch_variant<4>(c, p, t, nframes);
+    const int rc = S == 2 ? launch_variant<2>(c, p, t, nframes, a.early) : launch_variant<4>(c, p, t, nframes, a.early);
     if (rc) return rc;
     *done = true;
     return SRCNN_OK;

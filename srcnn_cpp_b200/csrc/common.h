@@ -138,6 +138,19 @@ struct Ctx {
     int* h_guard = nullptr;
 
     DevBuf plane_buf;   // Y, Cr, Cb, Y' planes (+ the FP16 Y plane)
+    DevBuf plane_buf2;  // the second plane set: consecutive device-resident whole-path calls alternate between the two, so that the
+                        // colour+bicubic kernel of call i+1 may run beside the merge kernel of call i (api.cu, "cross-call overlap")
+    int plane_sel = 0;               // plane set of the call being enqueued (0 / 1)
+    bool overlap = true;             // SRCNN_OVERLAP=0: one plane set, every kernel fully serialised (A/B aid)
+    int merge_ctas_per_sm = 4;       // grid of the merge kernel: CTAs of 256 threads per SM, each walking groups (SRCNN_MERGE_CTAS, tuning aid)
+    bool host_path = false;          // inside the host-buffer pipeline (its sub-bands share one plane set; may be under graph capture)
+    // the last merge kernel this context enqueued: the plane set it reads (-1: not a whole-path call's), the stream, and the
+    // bytes it writes -- what the next colour+bicubic launch must not touch if it is to start before that merge has finished
+    int merge_sel = -1;
+    long long early_launches = 0;    // colour+bicubic launches that were allowed to start early (srcnn_debug_overlap)
+    cudaStream_t merge_stream = nullptr;
+    const uint8_t* merge_lo = nullptr;
+    const uint8_t* merge_hi = nullptr;
     DevBuf y16_buf;     // stage API: FP16 copy of a caller's u8 Y plane
     DevBuf act2_buf;    // FP32 variant: conv2 activations (32 float planes) of one row chunk
     DevBuf src_buf;     // device copy of a host source image / batch
@@ -158,14 +171,16 @@ struct Ctx {
     bool use_graphs = true;          // SRCNN_GRAPHS=0 switches it off
     bool capturing = false;
 
-    // optional per-stage device timing (srcnn_profile_*): 4 events per band processed, prof_calls counts the API calls
-    bool profiling = false;
+    // optional per-stage device timing (srcnn_profile_*): 4 events per band processed (mode 1), or 2 -- around the CNN stage
+    // only -- in mode 2, which leaves merge(i) and colour+bicubic(i+1) adjacent in the stream (cross-call overlap stays on);
+    // prof_calls counts the API calls
+    int profiling = 0;
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
     int prof_calls = 0;
     int fail_stage = 0;              // which stage the last failed whole-path call died in (srcnn_last_failed_stage)
 };
-int prof_mark(Ctx* c);   // records the next event of the pool on c->stream when profiling is on
+int prof_mark(Ctx* c, int which);   // records the next event of the pool on c->stream when profiling is on (api.cu)
 
 int ensure(Ctx* c, DevBuf& b, size_t bytes);
 void drop_graphs(Ctx* c);
@@ -188,6 +203,7 @@ struct ResizeArgs {
     const TapTable* ty;
     int nframes = 1;      // same-sized frames in one launch, src_frame_stride / pl.frame_stride apart
     size_t src_frame_stride = 0;
+    bool early = false;   // may start while the previous kernel of the stream (a merge kernel of ours) is still running
 };
 int launch_color_bicubic(Ctx* c, const ResizeArgs& a);
 

@@ -644,6 +644,21 @@ __device__ __forceinline__ void role_loop(const Params& p, uint8_t* smem, const 
                 const uint32_t k = ybase + (uint32_t)q;
                 mbar_wait(ymb + (k & (kYSlots - 1)) * 8, (k >> 2) & 1u, wd, p.guard, 31);
             };
+            // A lane that lay beyond the image's right edge in the PREVIOUS segment (last strip of a frame) staged whatever bits the
+            // FP16 plane holds past its replicated columns -- possibly NaN or Inf patterns -- and they are still in the ring.  In this
+            // segment the lane may be a real column (a batch of frames: strip 0 of the next frame follows), and until a slot is
+            // rewritten conv1 multiplies it by zero weights: 0 x NaN = NaN in the first two rows.  So every segment but a pipeline's
+            // first starts from a finite ring, like the kernel does (the previous segment has drained: nothing reads the ring now).
+            if (!first_seg) {
+                uint32_t z[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) z[i] = 0u;
+#pragma unroll
+                for (int i = 0; i < 7; i++) tmem_st8(tml + kRingOff + 8 * i, z);
+                tc_wait_st();
+                tmem_st1(tml + kRingOff + kOnesCol, 0x3C003C00u);
+                tc_wait_st();
+            }
             uint32_t slot = slot0;
             uint32_t seen_f[4] = {0u, 0u, 0u, 0u}, seen_c = 0u;   // progress counters as seen one row ago
             uint32_t rot = slot0;                  // conv1 weight rotation = slot of the window's first ring row

@@ -63,3 +63,29 @@ def test_batch_in_one_launch_equals_frame_by_frame(engine, w, h, scale, n):
         engine.L.srcnn_debug_set_batch_launch(engine.ctx, 1)
     engine.sync()
     assert torch.equal(batch, one) and torch.equal(gappy, one) and torch.equal(loop, one)
+
+
+def test_batch_after_dirty_workspace(engine):
+    """A batch whose work list crosses frame boundaries inside one pipeline, run on a workspace that earlier, larger calls left
+    full of 0xFF bytes (NaN as FP16).  Lanes of a frame's last strip that lie beyond the image stage whatever the FP16 plane
+    holds past its replicated columns; the next segment of the same pipeline (strip 0 of the next frame) must not inherit those
+    bits through the im2col ring's zero-weight slots (0 x NaN = NaN in its first rows).  Regression test: found with frames of
+    160x90 after 700x400 frames, three rows of two frames wrong."""
+    import torch
+    rng = np.random.default_rng(77)
+    white = torch.from_numpy(rng.integers(250, 256, (400, 700, 3), dtype=np.uint8)).to("cuda:0")
+    big_out = torch.zeros((800, 1400, 3), dtype=torch.uint8, device="cuda:0")
+    for n in (6, 4, 5, 3):
+        for _ in range(2):                                   # both plane sets
+            engine.process_device(white, 2.0, big_out)
+        frames = torch.from_numpy(np.stack([natural_like(rng, 90, 160) for _ in range(n)])).to("cuda:0")
+        one = torch.zeros((n, 180, 320, 3), dtype=torch.uint8, device="cuda:0")
+        for k in range(n):
+            engine.process_device(frames[k], 2.0, one[k])
+        for _ in range(2):
+            engine.process_device(white, 2.0, big_out)
+        for rep in range(2):
+            batch = torch.zeros_like(one)
+            engine.process_batch_device(frames, 2.0, batch)
+            engine.sync()
+            assert torch.equal(batch, one), (n, rep)
