@@ -658,7 +658,7 @@ int srcnn_create(srcnn_ctx** out, int device, int variant) {
     if (const char* k = getenv("SRCNN_KA_ISR")) c->ka_int_isr = atoi(k);                                     // A/B aid
     if (const char* k = getenv("SRCNN_GRAPHS")) c->use_graphs = atoi(k) != 0;                                // A/B aid
     if (const char* k = getenv("SRCNN_OVERLAP")) c->overlap = atoi(k) != 0;                                  // A/B aid
-    if (const char* k = getenv("SRCNN_MERGE_CTAS")) c->merge_ctas_per_sm = std::max(1, std::min(8, atoi(k))); // tuning aid
+    if (const char* k = getenv("SRCNN_MERGE_CTAS")) c->merge_ctas_per_sm = std::max(0, std::min(64, atoi(k))); // tuning aid
     if (const char* k = getenv("SRCNN_BAND_FIRST")) c->band_first = std::max(0, atoi(k));                       // tuning aids: rows of the first
     if (const char* k = getenv("SRCNN_BAND_GROWTH")) c->band_growth = std::max(1.0, std::min(4.0, atof(k)));   // sub-band, growth per band
     if (const char* k = getenv("SRCNN_HOST_BANDS")) c->host_bands = std::max(1, std::min(64, atoi(k)));     // tuning aid

@@ -559,11 +559,11 @@ __device__ __forceinline__ uint32_t pack_sat_u8(int lo, int hi, uint32_t upper) 
     return d;
 }
 
-// A grid of at most a few CTAs per SM walks the 16-pixel groups of the image (row-major, grid-stride): every CTA is resident from
-// the start, so the kernel can let its dependents go at once (griddepcontrol.launch_dependents) -- the colour+bicubic kernel of
-// the NEXT whole-path call, when api.cu launched it with programmatic stream serialisation, then fills the SMs' free warp slots
-// while this kernel, which is bound by L2 / HBM and leaves the issue slots idle, is still running.  A kernel launched the
-// ordinary way waits for this one to finish as always.
+// Every CTA lets the kernel's dependents go on entry (griddepcontrol.launch_dependents): once the last CTA has started, the
+// colour+bicubic kernel of the NEXT whole-path call -- when api.cu launched it with programmatic stream serialisation -- fills the
+// SMs' free warp slots while this kernel, which is bound by L2 / HBM and leaves the issue slots idle, is still running.  A kernel
+// launched the ordinary way waits for this one to finish as always.  Threads walk the 16-pixel groups row-major with a grid stride
+// (one group per thread unless the grid is capped).
 __global__ void __launch_bounds__(256) k_merge_ycc2bgr_v16(const uint8_t* __restrict__ y, const uint8_t* __restrict__ cr,
                                                            const uint8_t* __restrict__ cb, size_t pitch, int w, int rows,
                                                            int swapRB, uint8_t* __restrict__ dst, size_t dst_stride,
@@ -646,9 +646,9 @@ int launch_merge(Ctx* c, const MergeArgs& a) {
     if (wide) {
         const int groups16 = (a.w + 15) / 16;
         const long long ngroups = (long long)groups16 * a.rows;
-        // every CTA resident at once (the kernel lets its dependents go on entry): kMergeCtasPerSm per SM at most
-        // ... and every thread gets the same number of groups (k), as far as the total allows
-        const long long want = (ngroups + 255) / 256, cap = (long long)c->merge_ctas_per_sm * std::max(1, c->sm_count);
+        // one group per thread by default (a thread that walks several groups is slower: common.h, merge_ctas_per_sm); the
+        // dependents are then released when the last CTA has started, roughly half-way through a 4K frame
+        const long long want = (ngroups + 255) / 256, cap = c->merge_ctas_per_sm > 0 ? (long long)c->merge_ctas_per_sm * std::max(1, c->sm_count) : want;
         const long long k = (want + cap - 1) / cap;
         const int grid = (int)((want + k - 1) / k);
         k_merge_ycc2bgr_v16<<<grid, 256, 0, c->stream>>>(a.y, a.cr, a.cb, a.pitch, a.w, a.rows, a.order == SRCNN_ORDER_RGB, a.dst,

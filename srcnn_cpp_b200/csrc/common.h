@@ -142,7 +142,8 @@ struct Ctx {
                         // colour+bicubic kernel of call i+1 may run beside the merge kernel of call i (api.cu, "cross-call overlap")
     int plane_sel = 0;               // plane set of the call being enqueued (0 / 1)
     bool overlap = true;             // SRCNN_OVERLAP=0: one plane set, every kernel fully serialised (A/B aid)
-    int merge_ctas_per_sm = 4;       // grid of the merge kernel: CTAs of 256 threads per SM, each walking groups (SRCNN_MERGE_CTAS, tuning aid)
+    int merge_ctas_per_sm = 0;       // merge kernel: 0 = one 16-pixel group per thread (fastest: 12.5 us per 4K frame, 6.4 TB/s on a 16K frame);
+                                     // n = at most n CTAs per SM, threads walk several groups (SRCNN_MERGE_CTAS, A/B aid: 14.0-14.5 us / 5.5-5.7 TB/s)
     bool host_path = false;          // inside the host-buffer pipeline (its sub-bands share one plane set; may be under graph capture)
     // the last merge kernel this context enqueued: the plane set it reads (-1: not a whole-path call's), the stream, and the
     // bytes it writes -- what the next colour+bicubic launch must not touch if it is to start before that merge has finished

@@ -31,7 +31,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --cs
     python bench.py --steps 4 --warmup 3 --no-cpu > gpurun_out/prof_bench.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_srcnn_tc2 -s 3 -c 1 -f -o gpurun_out/prof_tc2 \
     python bench.py --steps 4 --warmup 3 --no-cpu >> gpurun_out/prof_bench.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_color_bicubic_tiled -s 3 -c 1 -f -o gpurun_out/prof_a \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_color_bicubic -s 3 -c 1 -f -o gpurun_out/prof_a \
     python bench.py --steps 4 --warmup 3 --no-cpu >> gpurun_out/prof_bench.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_merge_ycc2bgr -s 3 -c 1 -f -o gpurun_out/prof_c \
     python bench.py --steps 4 --warmup 3 --no-cpu >> gpurun_out/prof_bench.log 2>&1
