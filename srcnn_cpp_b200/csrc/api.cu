@@ -80,9 +80,12 @@ static int check_image(Ctx* c, const void* src, int w, int h, size_t stride, int
 }
 
 // planes of `nframes` same-sized frames: [Y frames][Cr frames][Cb frames][Y' frames][FP16 Y frames]
-// Cross-call overlap: device-resident whole-path calls alternate between two plane sets (when a set is at most 8 GiB), so
-// that nothing the colour+bicubic kernel of call i+1 writes is read by the merge kernel of call i; c->plane_sel says which
-// set this call got.  The host-buffer pipeline keeps to set 0 (its sub-bands are separated by copies and events anyway).
+// Cross-call overlap: the only planes the colour+bicubic kernel of call i+1 writes AND the merge kernel of call i reads are Cr and
+// Cb, so device-resident whole-path calls alternate between two Cr/Cb pairs (the second in plane_buf2, when a pair is at most
+// 4 GiB); Y, Y' and the FP16 Y plane are shared (the merge never reads Y / FP16 Y, and Y' is written by the next CNN launch, which
+// waits for everything before it).  c->plane_sel says which pair this call got.  Keeping the rest single also keeps the planes
+// L2-resident from step to step: two whole plane sets (116 MB at 4K) measured 3 us slower in the colour+bicubic kernel.
+// The host-buffer pipeline keeps to pair 0 (its sub-bands are separated by copies and events anyway).
 static int carve_planes(Ctx* c, int ow, int rows, int row0, Planes* pl, int nframes = 1) {
     const size_t pitch = align_up((size_t)ow, 128);
     const size_t plane = pitch * (size_t)rows;
@@ -90,15 +93,16 @@ static int carve_planes(Ctx* c, int ow, int rows, int row0, Planes* pl, int nfra
     const size_t plane16 = align_up(pitch16 * (size_t)rows, 256);
     const size_t nf = (size_t)nframes;
     const size_t bytes = (plane * 4 + plane16) * nf + 512;   // slack: the last row's last strip copy may run past the row
-    const bool two = c->overlap && !c->host_path && !c->capturing && bytes <= ((size_t)8 << 30);
+    const bool two = c->overlap && !c->host_path && !c->capturing && plane * 2 * nf <= ((size_t)4 << 30);
     c->plane_sel = two ? (c->plane_sel ^ 1) : 0;
-    DevBuf& buf = c->plane_sel ? c->plane_buf2 : c->plane_buf;
-    int rc = ensure(c, buf, bytes);
+    int rc = ensure(c, c->plane_buf, bytes);
     if (rc) return rc;
-    uint8_t* base = (uint8_t*)buf.p;
+    if (c->plane_sel && (rc = ensure(c, c->plane_buf2, plane * 2 * nf))) return rc;
+    c->plane_layout[0] = pitch; c->plane_layout[1] = (size_t)rows; c->plane_layout[2] = nf;
+    uint8_t* base = (uint8_t*)c->plane_buf.p;
     pl->y = base;
-    pl->cr = base + plane * nf;
-    pl->cb = base + 2 * plane * nf;
+    pl->cr = c->plane_sel ? (uint8_t*)c->plane_buf2.p : base + plane * nf;
+    pl->cb = c->plane_sel ? (uint8_t*)c->plane_buf2.p + plane * nf : base + 2 * plane * nf;
     pl->yout = base + 3 * plane * nf;
     pl->y16 = base + 4 * plane * nf;
     pl->frame_stride = plane;
@@ -117,10 +121,14 @@ static int carve_planes(Ctx* c, int ow, int rows, int row0, Planes* pl, int nfra
 static bool may_start_early(Ctx* c, const uint8_t* src, size_t src_bytes) {
     if (!c->overlap || c->host_path || c->capturing || c->profiling == 1) return false;
     if (c->merge_sel < 0 || c->merge_sel == c->plane_sel || c->merge_stream != c->stream) return false;
+    // same plane geometry as that call: Y, Y' and the FP16 Y plane are shared, and another layout of the same buffer could put this
+    // call's Y where that merge still reads its Y'
+    if (c->merge_layout[0] != c->plane_layout[0] || c->merge_layout[1] != c->plane_layout[1] || c->merge_layout[2] != c->plane_layout[2]) return false;
     return src + src_bytes <= c->merge_lo || src >= c->merge_hi;
 }
 static void merged_into(Ctx* c, const uint8_t* dst, size_t bytes) {   // after the whole-path call's (last) launch_merge
     c->merge_sel = c->plane_sel;
+    for (int i = 0; i < 3; i++) c->merge_layout[i] = c->plane_layout[i];
     c->merge_stream = c->stream;
     c->merge_lo = dst;
     c->merge_hi = dst + bytes;

@@ -138,9 +138,9 @@ struct Ctx {
     int* h_guard = nullptr;
 
     DevBuf plane_buf;   // Y, Cr, Cb, Y' planes (+ the FP16 Y plane)
-    DevBuf plane_buf2;  // the second plane set: consecutive device-resident whole-path calls alternate between the two, so that the
-                        // colour+bicubic kernel of call i+1 may run beside the merge kernel of call i (api.cu, "cross-call overlap")
-    int plane_sel = 0;               // plane set of the call being enqueued (0 / 1)
+    DevBuf plane_buf2;  // a second Cr/Cb pair: consecutive device-resident whole-path calls alternate between the two, so that the
+                        // colour+bicubic kernel of call i+1 may run beside the merge kernel of call i (api.cu, carve_planes)
+    int plane_sel = 0;               // Cr/Cb pair of the call being enqueued (0 / 1)
     bool overlap = true;             // SRCNN_OVERLAP=0: one plane set, every kernel fully serialised (A/B aid)
     int merge_ctas_per_sm = 0;       // merge kernel: 0 = one 16-pixel group per thread (fastest: 12.5 us per 4K frame, 6.4 TB/s on a 16K frame);
                                      // n = at most n CTAs per SM, threads walk several groups (SRCNN_MERGE_CTAS, A/B aid: 14.0-14.5 us / 5.5-5.7 TB/s)
@@ -148,6 +148,7 @@ struct Ctx {
     // the last merge kernel this context enqueued: the plane set it reads (-1: not a whole-path call's), the stream, and the
     // bytes it writes -- what the next colour+bicubic launch must not touch if it is to start before that merge has finished
     int merge_sel = -1;
+    size_t plane_layout[3] = {0, 0, 0}, merge_layout[3] = {0, 0, 0};   // (pitch, rows, frames) of the current carve / of that merge's
     long long early_launches = 0;    // colour+bicubic launches that were allowed to start early (srcnn_debug_overlap)
     cudaStream_t merge_stream = nullptr;
     const uint8_t* merge_lo = nullptr;

@@ -42,7 +42,7 @@ def test_back_to_back_calls_equal_serialised_calls(engine, variant_name):
             engine.sync()
             for a, b in zip(ref, got):
                 assert torch.equal(a, b)
-        assert _overlap(engine, -1) - early0 >= 3 * 5     # every call after another whole-path call was allowed to start early
+        assert _overlap(engine, -1) - early0 >= 3 * 2     # a call that follows one of the same plane geometry was allowed to start early
     finally:
         _overlap(engine, 1)
         engine.set_variant(S.VARIANT_TC)
