@@ -20,8 +20,13 @@ synthetic input:
                more frame/result buffers than fit in L2, the other configurations are far larger than L2 per step
   e2e        : the same metric through the host-buffer C-ABI calls with pinned HOST buffers: H2D of the input and D2H of
                the result are inside the timed region of every step
-  roofline   : fused SRCNN kernel, 16 064 algorithmic FLOP per output pixel / its CUDA-event duration, against
-               MEASURED_PEAKS.json's dense bf16 burst figure (same tensor rate as fp16); the sustained figure beside it
+  roofline   : fused SRCNN kernel, 16 064 algorithmic FLOP per output pixel / its CUDA-event duration (events around every
+               launch of the timed region, on the launching stream), against MEASURED_PEAKS.json's dense bf16 burst figure
+               (same tensor rate as fp16); the sustained figure beside it
+  stages     : the two HBM-bound kernels are timed in a short SERIALISED pass after the timed region (events around every
+               stage): in the timed region the merge of step i and the colour+bicubic of step i+1 run side by side (the
+               library's cross-call overlap), and an event between them would separate them; `between_srcnn_launches_ms` is
+               what the pair costs there
   cpu_baseline: the reference's CPU code (oracle/_ref/libref.so + cv2, IPP off) on the box's host cores, on a bounded
                sample of the same workload
 """

@@ -5,7 +5,10 @@
 // No CPU fallback exists anywhere in this file: every path ends in a kernel launch or an error.
 #include <cstdarg>
 #include <cstdlib>
+#include <iterator>
+#include <mutex>
 #include <new>
+#include <unordered_map>
 
 #include "common.h"
 
@@ -114,6 +117,25 @@ static int carve_planes(Ctx* c, int ow, int rows, int row0, Planes* pl, int nfra
     return SRCNN_OK;
 }
 
+// Which context enqueued the most recent merge kernel on a stream (process-wide: a caller may run several contexts on one stream
+// and feed one's result to the other).
+static std::mutex g_merge_mu;
+static std::unordered_map<cudaStream_t, Ctx*> g_last_merge;
+void note_merge(Ctx* c) {
+    std::lock_guard<std::mutex> lk(g_merge_mu);
+    g_last_merge[c->stream] = c;
+}
+static Ctx* last_merge_on(cudaStream_t s) {
+    std::lock_guard<std::mutex> lk(g_merge_mu);
+    auto it = g_last_merge.find(s);
+    return it == g_last_merge.end() ? nullptr : it->second;
+}
+static void forget_merges_of(Ctx* c) {
+    std::lock_guard<std::mutex> lk(g_merge_mu);
+    for (auto it = g_last_merge.begin(); it != g_last_merge.end();)
+        it = it->second == c ? g_last_merge.erase(it) : std::next(it);
+}
+
 // May the colour+bicubic kernel about to be enqueued start while the stream's previous kernel is still running?  Only when that
 // kernel is a merge of ours (launch_merge lets its dependents go at once) which reads the OTHER plane set and writes nothing
 // this call's source overlaps (a caller may feed one call's result to the next).  Anything the caller put on the stream in
@@ -121,6 +143,7 @@ static int carve_planes(Ctx* c, int ow, int rows, int row0, Planes* pl, int nfra
 static bool may_start_early(Ctx* c, const uint8_t* src, size_t src_bytes) {
     if (!c->overlap || c->host_path || c->capturing || c->profiling == 1) return false;
     if (c->merge_sel < 0 || c->merge_sel == c->plane_sel || c->merge_stream != c->stream) return false;
+    if (last_merge_on(c->stream) != c) return false;   // another context of the process has put a merge on this stream since: its result is unknown here
     // same plane geometry as that call: Y, Y' and the FP16 Y plane are shared, and another layout of the same buffer could put this
     // call's Y where that merge still reads its Y'
     if (c->merge_layout[0] != c->plane_layout[0] || c->merge_layout[1] != c->plane_layout[1] || c->merge_layout[2] != c->plane_layout[2]) return false;
@@ -678,6 +701,7 @@ int srcnn_destroy(srcnn_ctx* c) {
     if (!c) return SRCNN_E_ARG;
     srcnn::DeviceScope scope(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    forget_merges_of(c);
     drop_graphs(c);
     tc2_release(c);
     fraw_release(c);

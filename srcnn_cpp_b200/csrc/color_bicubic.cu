@@ -642,7 +642,8 @@ int launch_merge(Ctx* c, const MergeArgs& a) {
     if (a.rows <= 0 || a.w <= 0) return SRCNN_OK;
     const bool wide = ((((uintptr_t)a.dst) | a.dst_stride | (uintptr_t)a.y | (uintptr_t)a.cr | (uintptr_t)a.cb | a.pitch) & 15) == 0 &&
                       a.pitch >= align_up((size_t)a.w, 16);
-    c->merge_sel = -1;   // a whole-path caller says afterwards which plane set this launch reads (api.cu, merged_into)
+    c->merge_sel = -1;   // a whole-path caller says afterwards which Cr/Cb pair this launch reads (api.cu, merged_into)
+    note_merge(c);
     if (wide) {
         const int groups16 = (a.w + 15) / 16;
         const long long ngroups = (long long)groups16 * a.rows;

@@ -220,6 +220,7 @@ struct MergeArgs {
     size_t dst_stride;
 };
 int launch_merge(Ctx* c, const MergeArgs& a);
+void note_merge(Ctx* c);   // api.cu: this context has just put a merge kernel (which releases its dependents early) on its stream
 // u8 Y plane -> FP16 plane in the Planes::y16 layout (replicated edge columns included)
 int launch_y8_to_y16(Ctx* c, const uint8_t* y, size_t pitch, int w, int rows, uint8_t* y16, size_t pitch16);
 

@@ -114,3 +114,32 @@ def test_profile_mode_2_times_the_cnn_stage_and_the_gaps(engine):
     finally:
         engine.profile_enable(False)
     assert calls1 == 6 and min(ms1) > 0
+
+
+def test_two_contexts_on_one_stream_chained(engine):
+    """A second context on the same stream whose source is the first context's result: the early start is refused (the second
+    context cannot know what the first one's merge writes)."""
+    import torch
+    import srcnn_cpp_b200 as S
+    rng = np.random.default_rng(9)
+    img = torch.from_numpy(natural_like(rng, 180, 256)).to("cuda:0")
+    eng2 = S.Engine(device=0, variant=S.VARIANT_TC, stream=torch.cuda.current_stream().cuda_stream)   # the fixture's stream
+    try:
+        mid0 = torch.zeros((360, 512, 3), dtype=torch.uint8, device="cuda:0")
+        out0 = torch.zeros((720, 1024, 3), dtype=torch.uint8, device="cuda:0")
+        _overlap(engine, 0)
+        engine.process_device(img, 2.0, mid0)
+        engine.sync()
+        eng2.process_device(mid0, 2.0, out0)
+        eng2.sync()
+        _overlap(engine, 1)
+        other = torch.zeros((720, 1024, 3), dtype=torch.uint8, device="cuda:0")
+        for rep in range(4):
+            mid, out = torch.zeros_like(mid0), torch.zeros_like(out0)
+            eng2.process_device(mid0, 2.0, other)     # eng2's own previous call: same geometry, unrelated buffers
+            engine.process_device(img, 2.0, mid)
+            eng2.process_device(mid, 2.0, out)        # reads what engine's merge is writing
+            eng2.sync()
+            assert torch.equal(mid, mid0) and torch.equal(out, out0)
+    finally:
+        eng2.close()
