@@ -75,17 +75,22 @@ def test_batch_after_dirty_workspace(engine):
     rng = np.random.default_rng(77)
     white = torch.from_numpy(rng.integers(250, 256, (400, 700, 3), dtype=np.uint8)).to("cuda:0")
     big_out = torch.zeros((800, 1400, 3), dtype=torch.uint8, device="cuda:0")
-    for n in (6, 4, 5, 3):
-        for _ in range(2):                                   # both plane sets
+    import srcnn_cpp_b200 as S
+    # (w, h, scale, frames): the geometry of the find; one strip exactly (2 lanes beyond the image); a last strip of 4 columns;
+    # a x3 up-scale and a width that is no multiple of 8 (generic colour+bicubic kernel)
+    for w, h, scale, n in ((160, 90, 2.0, 6), (160, 90, 2.0, 4), (160, 90, 2.0, 5), (160, 90, 2.0, 3), (62, 40, 2.0, 9), (250, 70, 2.0, 5),
+                           (100, 60, 3.0, 4), (333, 50, 2.0, 3)):
+        ow, oh = S.out_dims(w, h, scale)
+        for _ in range(2):                                   # both Cr/Cb pairs
             engine.process_device(white, 2.0, big_out)
-        frames = torch.from_numpy(np.stack([natural_like(rng, 90, 160) for _ in range(n)])).to("cuda:0")
-        one = torch.zeros((n, 180, 320, 3), dtype=torch.uint8, device="cuda:0")
+        frames = torch.from_numpy(np.stack([natural_like(rng, h, w) for _ in range(n)])).to("cuda:0")
+        one = torch.zeros((n, oh, ow, 3), dtype=torch.uint8, device="cuda:0")
         for k in range(n):
-            engine.process_device(frames[k], 2.0, one[k])
+            engine.process_device(frames[k], scale, one[k])
         for _ in range(2):
             engine.process_device(white, 2.0, big_out)
         for rep in range(2):
             batch = torch.zeros_like(one)
-            engine.process_batch_device(frames, 2.0, batch)
+            engine.process_batch_device(frames, scale, batch)
             engine.sync()
-            assert torch.equal(batch, one), (n, rep)
+            assert torch.equal(batch, one), (w, h, scale, n, rep)
