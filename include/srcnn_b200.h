@@ -92,6 +92,10 @@ int srcnn_device_sm_count(srcnn_ctx* ctx);
  * [0] colour+bicubic, [1] fused SRCNN, [2] merge+colour-back over everything processed since the
  * previous read, and the number of whole-path API calls that work came from (a batch or a banded
  * call counts once, however many frames or bands it ran). */
+/* on = 1: events around all three stages (the stages of consecutive calls then run strictly one after another);
+ * on = 2: events around the CNN stage only, so that the merge kernel of one call and the colour+bicubic kernel of the next stay
+ *         adjacent in the stream and may overlap (DESIGN.md "Cross-call overlap"): srcnn_profile_read then returns
+ *         [0] the summed time BETWEEN consecutive CNN launches, [1] the CNN stage, [2] 0. */
 int srcnn_profile_enable(srcnn_ctx* ctx, int on);
 int srcnn_profile_read(srcnn_ctx* ctx, double* ms3, int* calls);
 
@@ -108,7 +112,10 @@ int srcnn_host_unregister(void* p);
 /* Host buffers in, host buffers out; H2D and D2H copies are part of the call; returns when dst is ready. */
 int srcnn_process_host(srcnn_ctx* ctx, const uint8_t* src, int w, int h, size_t src_stride, int order,
                        float scale, uint8_t* dst, size_t dst_stride);
-/* Device buffers; enqueued on the context stream, returns without synchronising. */
+/* Device buffers; enqueued on the context stream, returns without synchronising.  Ordinary stream semantics: ordered after
+ * everything the caller enqueued before the call, complete when the stream reaches the point after it.  (Between two whole-path
+ * calls that follow each other directly the library may run the second call's first kernel beside the first call's last one --
+ * never when the second call's source overlaps the first call's result; SRCNN_OVERLAP=0 switches that off.) */
 int srcnn_process_device(srcnn_ctx* ctx, const uint8_t* d_src, int w, int h, size_t src_stride, int order,
                          float scale, uint8_t* d_dst, size_t dst_stride);
 /* n same-sized frames, frame f at base + f*frame_stride (bytes).  Device or host variants. */
