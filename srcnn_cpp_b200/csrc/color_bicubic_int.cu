@@ -26,8 +26,11 @@ namespace srcnn {
 
 namespace {
 
+// x2 instance: minimum CTAs per SM the register allocation is held to.  Same-box A/B inside the bench step (tools/ab_bench_libs.sh):
+// 9 (72 registers, 96 B of spills in the walk) 49.1 GPix/s, 8 (80 registers, 32 B) 49.5-49.8, 6 (91 registers, none) 49.9 -- but
+// 1 % slower than 8 in many-wave launches (1024 720p frames: 8.33 vs 8.24 ms); 10 (64 registers) 48.5.
 #ifndef SRCNN_KA_MINB
-#define SRCNN_KA_MINB 9
+#define SRCNN_KA_MINB 8
 #endif
 constexpr int kISRMax = 16;         // most source rows a tile advances by (IntTaps::isr; plus 3 rows of apron staged with them)
 constexpr int kIRows = kISRMax + 3;
