@@ -32,6 +32,9 @@ namespace {
 #ifndef SRCNN_KA_MINB
 #define SRCNN_KA_MINB 8
 #endif
+#ifndef SRCNN_KA_MINB4
+#define SRCNN_KA_MINB4 5         // x4 instance: 126 registers, no spills -- 168.7 vs 174.6 us per 4K -> 16K frame with 6 (96 registers, 64 B of spills)
+#endif
 constexpr int kISRMax = 16;         // most source rows a tile advances by (IntTaps::isr; plus 3 rows of apron staged with them)
 constexpr int kIRows = kISRMax + 3;
 constexpr int kIPitch = 144;       // bytes per converted row: 34 four-pixel groups + one spare word for the 3-word window read
@@ -234,7 +237,7 @@ __device__ __forceinline__ void walk_tile(const ResizeDev& p, const IntTaps& t, 
 // The kernel: one CTA of 3 warps per tile.
 // ------------------------------------------------------------------------------------------------
 template <int S>
-__global__ void __launch_bounds__(96, S == 2 ? SRCNN_KA_MINB : 6) k_color_bicubic_int(const ResizeDev p, const IntTaps t) {
+__global__ void __launch_bounds__(96, S == 2 ? SRCNN_KA_MINB : SRCNN_KA_MINB4) k_color_bicubic_int(const ResizeDev p, const IntTaps t) {
     constexpr int G = Geo<S>::G;
     __shared__ __align__(16) uint8_t sP[3][kIRows][kIPitch];
     const int tid = threadIdx.x;
