@@ -137,7 +137,7 @@ static void forget_merges_of(Ctx* c) {
 }
 
 // May the colour+bicubic kernel about to be enqueued start while the stream's previous kernel is still running?  Only when that
-// kernel is a merge of ours (launch_merge lets its dependents go at once) which reads the OTHER plane set and writes nothing
+// kernel is a merge of ours (launch_merge lets its dependents go at once) which reads the OTHER Cr/Cb pair and writes nothing
 // this call's source overlaps (a caller may feed one call's result to the next).  Anything the caller put on the stream in
 // between simply keeps the usual order: the early start is a property of two adjacent kernels (programmatic dependent launch).
 static bool may_start_early(Ctx* c, const uint8_t* src, size_t src_bytes) {
@@ -478,7 +478,7 @@ static int enqueue_chunk(Ctx* c, const uint8_t* src, int f0, int m, int w, int h
 int host_pipeline(Ctx* c, const uint8_t* src, int n, int w, int h, size_t src_stride, size_t src_frame_stride, int order,
                   float scale, int ow, int oh, int R0, int R1, uint8_t* dst, size_t dst_stride, size_t dst_frame_stride) {
     int rc;
-    struct HostPath {   // the pipeline's sub-bands and groups share plane set 0 (carve_planes) and never start early
+    struct HostPath {   // the pipeline's sub-bands and groups share Cr/Cb pair 0 (carve_planes) and never start early
         Ctx* c;
         explicit HostPath(Ctx* c_) : c(c_) { c->host_path = true; c->merge_sel = -1; }
         ~HostPath() { c->host_path = false; c->merge_sel = -1; }
@@ -770,7 +770,7 @@ extern "C" __attribute__((visibility("default"))) int srcnn_debug_set_batch_laun
     c->batch_launch = on != 0;
     return SRCNN_OK;
 }
-// test hook: cross-call overlap (two plane sets; colour+bicubic of call i+1 beside the merge of call i) on / off; returns
+// test hook: cross-call overlap (two Cr/Cb pairs; colour+bicubic of call i+1 beside the merge of call i) on / off; returns
 // how many colour+bicubic launches so far were allowed to start early
 extern "C" __attribute__((visibility("default"))) long long srcnn_debug_overlap(srcnn_ctx* c, int on) {
     if (!c) return SRCNN_E_ARG;
